@@ -1,0 +1,157 @@
+/*
+ * b200sdr.h -- C ABI of libb200sdr.so: the B200-native (sm_100a) IQ processing path for
+ * rtl-ws.  Plain C, plain pointers and sizes; no CUDA or torch types appear in any
+ * signature (a CUDA stream is passed as an opaque `void*`, NULL = the default stream).
+ *
+ * Two layers are exported:
+ *
+ *   1. The reference's own DSP interface, symbol for symbol (include/rtlws_compat.h):
+ *      spectrum_*, rf_decimator_*, cic_decimate, halfband_decimate.  An unmodified
+ *      cbb_main.c / audio_main.c / main.c links against this library instead of the
+ *      reference's spectrum.o / rf_decimator.o / resample.o.
+ *
+ *   2. The batched / streaming extension declared here (SURVEY.md section 8b "required
+ *      extension"), which is what carries throughput: many frames and many independent
+ *      dongle streams per launch, device-resident or fed from pinned host rings.
+ *
+ * Every entry point names the reference code whose arithmetic it reproduces
+ * (paths relative to the reference's src/).  Results match that code bit-for-bit for
+ * integer stages and within the tolerances of BASELINE.json for floating point.
+ * There is no CPU fallback: without a usable CUDA device every call fails with
+ * B200_ERR_CUDA and b200_last_error() says why.
+ */
+#ifndef B200SDR_H
+#define B200SDR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_ARG (-1)     /* size / parameter mismatch (the reference's -1) */
+#define B200_ERR_OVERRUN (-2) /* internal overrun (the reference's -2) */
+#define B200_ERR_CUDA (-3)    /* CUDA runtime failure or no device; see b200_last_error() */
+#define B200_ERR_ALIGN (-4)   /* pointer / stride / hop not aligned as documented */
+
+/* ---- library ------------------------------------------------------------------------ */
+
+/* Selects the CUDA device for the calling thread and warms the context.  Optional: every
+ * other call initialises lazily on the current device. */
+int b200_init(int device);
+/* Last error text of the calling thread ("" if none). */
+const char* b200_last_error(void);
+/* Number of kernel launches issued by this library since load (all threads). */
+uint64_t b200_launch_count(void);
+/* SM count of the current device (grid sizing is a multiple of it). */
+int b200_sm_count(void);
+
+/* ---- batched power spectrum ------------------------------------------------------------
+ *
+ * Replaces, for many frames at once:
+ *   spectrum.c:47-58   u8 -> ((x - 128) / 128) unpack           (+ optional window, extension)
+ *   spectrum.c:21      fftw_execute: unnormalised forward DFT, N points
+ *   spectrum.c:23-34   fftshift, |X|^2, accumulate, DC-position patch
+ *   cbb_main.c:48-59   "zero a row, add K frames"
+ *   cbb_main.c:112-128 10*log10(|g * P / K|) -> float dB and/or truncated+clamped u8
+ *
+ * Geometry of one stream:  output row r accumulates the K frames that start at sample
+ *   r * row_hop + j * hop,  j = 0..K-1   (reference: hop = N, K <= 6, row_hop = one source
+ *   buffer cadence; per-frame spectra: K = 1, row_hop = hop = N; 50% overlap: hop = N/2).
+ * hop and row_hop must be multiples of 8 samples (16-byte TMA alignment).
+ */
+typedef struct b200_spectrum_plan b200_spectrum_plan;
+
+#define B200_WINDOW_RECT 0   /* the reference */
+#define B200_WINDOW_HANN 1   /* periodic Hann, extension */
+
+/* N: a power of two in [16, 65536] (1024 has a specialised kernel).  gain_db follows cbb_main.c:112 (integer division by 10). */
+b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row_hop, int window, int gain_db);
+void b200_spectrum_plan_destroy(b200_spectrum_plan* plan);
+/* Rows that fit in a stream of n_samples. */
+int64_t b200_spectrum_plan_rows(const b200_spectrum_plan* plan, int64_t n_samples);
+
+/*
+ * Device-resident execution.  d_iq: interleaved u8 IQ (cmplx_u8 layout, common_sp.h:7-11),
+ * stream s starts at d_iq + s * stream_stride_bytes (16-byte aligned).  Outputs are
+ * [n_streams][n_rows][N] in display order (index 0 = -fs/2, N/2 = DC position), any of them
+ * may be NULL:  d_db float dB, d_power float linear power summed over the K frames (the
+ * reference's power_spectrum array), d_db_u8 the payload bytes of cbb_main.c:125-128.
+ */
+int b200_spectrum_exec(b200_spectrum_plan* plan, const uint8_t* d_iq, int64_t stream_stride_bytes,
+                       int n_streams, int64_t n_rows,
+                       float* d_db, float* d_power, uint8_t* d_db_u8, void* cuda_stream);
+
+/* Same, for the reference's other two input types (spectrum.c:65-99; no callers in the
+ * reference, kept for interface completeness).  cs32: interleaved int32 (re, im), scaled by
+ * 1/128 like the u8 path; rf32: real float samples, imaginary part 0, no scaling.
+ * Strides are in bytes; frame geometry (hop, row_hop) is in samples of the given type. */
+int b200_spectrum_exec_cs32(b200_spectrum_plan* plan, const int32_t* d_iq, int64_t stream_stride_bytes,
+                            int n_streams, int64_t n_rows,
+                            float* d_db, float* d_power, uint8_t* d_db_u8, void* cuda_stream);
+int b200_spectrum_exec_rf32(b200_spectrum_plan* plan, const float* d_x, int64_t stream_stride_bytes,
+                            int n_streams, int64_t n_rows,
+                            float* d_db, float* d_power, uint8_t* d_db_u8, void* cuda_stream);
+
+/* ---- FM branch: CIC decimation -> discriminator -> two half-band decimators --------------
+ *
+ * Replaces, fused in one pass over the IQ bytes:
+ *   resample.c:6-45     cic_decimate (boxcar sum of R samples minus 128*R, exact int32)
+ *   common_sp.h:40-76   atan2_approx
+ *   audio_main.c:110-131 first difference (no unwrap) and +-1 hard limiter
+ *   resample.c:47-67    halfband_decimate, twice (audio_main.c:133,139)
+ * One audio sample per 4*R input samples.
+ *
+ * State carry: instead of the reference's delay structs (rf_decimator.c:28,
+ * audio_main.c:77-79) a stream carries its last b200_fm_history_samples(R) INPUT samples.
+ * The caller lays every stream out as [history | batch] and passes the pointer to the batch;
+ * a new stream's history is all 128 (b200_fm_history_reset), which reproduces the
+ * reference's zero-initialised state exactly, and b200_fm_history_carry copies the batch
+ * tail over the history after each batch.  n_samples must be a multiple of 4*R and of 8.
+ */
+int b200_fm_history_samples(int R);
+int b200_fm_history_reset(uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams, int R, void* cuda_stream);
+int b200_fm_history_carry(uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams, int64_t n_samples,
+                          int R, void* cuda_stream);
+/* d_audio: [n_streams][n_samples / (4R)] floats, row stride audio_stride (floats).
+ * d_decimated (nullable): [n_streams][n_samples / R] cmplx_s32, row stride dec_stride (complex). */
+int b200_fm_exec(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams, int64_t n_samples, int R,
+                 float* d_audio, int64_t audio_stride, int32_t* d_decimated, int64_t dec_stride,
+                 void* cuda_stream);
+
+/* ---- the full chain on the same IQ, read once ---------------------------------------------
+ *
+ * N = 1024 per-frame spectra (K = 1, hop = row_hop = 1024, rectangular: the reference's
+ * FFT_POINTS and window) fused with the FM branch at R = 10 (cbb_main.c:80 at 2.048 MS/s).
+ * n_samples must be a multiple of 5120 (5 frames = 128 audio samples).  Layout and history
+ * as for b200_fm_exec; d_db: [n_streams][n_samples/1024][1024] float dB (display order).
+ * d_avg_u8 (nullable): [n_streams][1024] payload bytes of the K_avg-frame average that
+ * starts at frame 0 of the batch (the spectrum a UI client would be sent), written
+ * directly into the caller's gather/send buffer.
+ */
+int b200_chain_exec(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams, int64_t n_samples,
+                    int gain_db, float* d_db, float* d_audio, int64_t audio_stride,
+                    uint8_t* d_avg_u8, int K_avg, void* cuda_stream);
+
+/* ---- host-buffer entry point (what a plugin calls; includes the PCIe copies) --------------
+ *
+ * Same work as b200_chain_exec for HOST buffers: the library stages the IQ through its own
+ * device ring with asynchronous copies on several CUDA streams, runs the kernels and
+ * copies the results back.  h_iq: [n_streams][n_samples] cmplx_u8 batch (no history: the
+ * session keeps it), h_db / h_audio as above (either may be NULL).  Pinned host memory
+ * (b200_host_alloc) makes the copies asynchronous; pageable memory works but serialises.
+ */
+typedef struct b200_session b200_session;
+b200_session* b200_session_create(int n_streams, int64_t max_samples_per_batch);
+void b200_session_destroy(b200_session* s);
+void b200_session_reset(b200_session* s);      /* all streams back to stream start */
+int b200_session_chain(b200_session* s, const uint8_t* h_iq, int64_t n_samples, int gain_db,
+                       float* h_db, float* h_audio);
+void* b200_host_alloc(uint64_t bytes);          /* pinned host memory */
+void b200_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

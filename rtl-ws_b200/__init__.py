@@ -1,0 +1,16 @@
+"""rtl-ws_b200 -- B200-native (sm_100a) IQ processing path for rtl-ws.
+
+The product is the C-ABI shared library ``libb200sdr.so`` built from ``csrc/`` (CUDA
+kernels + host C++); this package is its thin ctypes binding plus the synthetic IQ
+generators used by the tests and the benchmark.  The directory name carries a hyphen, so
+import it through ``__graft_entry__.load_package()`` (tests/conftest.py does) under the
+module name ``rtl_ws_b200``.
+"""
+from . import binding, synth  # noqa: F401
+from .binding import (  # noqa: F401
+    B200Error, SpectrumPlan, StreamRing, Session, RfDecimator, CicDelayLine,
+    fm_exec, chain_exec, init, lib, launch_count,
+    spectrum_alloc, spectrum_free, spectrum_add_cmplx_u8, spectrum_add_cmplx_s32, spectrum_add_real_f32,
+    cic_decimate, halfband_decimate,
+    WINDOW_RECT, WINDOW_HANN, CHAIN_TILE, LIB_PATH, EXPORTED_SYMBOLS,
+)

@@ -1,0 +1,391 @@
+"""ctypes binding of libb200sdr.so (include/b200sdr.h, include/rtlws_compat.h).
+
+PyTorch is used for device memory and streams only; every computation happens inside the
+library's CUDA kernels.  There is no fallback: if the shared library is missing or the
+machine has no CUDA device, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200sdr.so")
+
+WINDOW_RECT = 0
+WINDOW_HANN = 1
+
+CHAIN_TILE = 5120          # samples: 5 frames of 1024 = 128 audio samples at R = 10
+HALF_BAND_N = 11
+
+# every symbol include/b200sdr.h and include/rtlws_compat.h declare
+EXPORTED_SYMBOLS = [
+    "b200_init", "b200_last_error", "b200_launch_count", "b200_sm_count",
+    "b200_spectrum_plan_create", "b200_spectrum_plan_destroy", "b200_spectrum_plan_rows", "b200_spectrum_exec",
+    "b200_spectrum_exec_cs32", "b200_spectrum_exec_rf32",
+    "b200_fm_history_samples", "b200_fm_history_reset", "b200_fm_history_carry", "b200_fm_exec",
+    "b200_chain_exec",
+    "b200_session_create", "b200_session_destroy", "b200_session_reset", "b200_session_chain",
+    "b200_host_alloc", "b200_host_free",
+    "spectrum_alloc", "spectrum_add_cmplx_u8", "spectrum_add_cmplx_s32", "spectrum_add_real_f32", "spectrum_free",
+    "cic_decimate", "halfband_decimate",
+    "rf_decimator_alloc", "rf_decimator_add_callback", "rf_decimator_set_parameters",
+    "rf_decimator_decimate_cmplx_u8", "rf_decimator_remove_callbacks", "rf_decimator_free",
+]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class CmplxS32(C.Structure):
+    _fields_ = [("re", C.c_int32), ("im", C.c_int32)]
+
+
+class CicDelayLine(C.Structure):
+    """struct cic_delay_line (resample.h:8-12)."""
+    _fields_ = [("integrator_prev_out", CmplxS32), ("comb_prev_in", CmplxS32)]
+
+
+RF_CALLBACK = C.CFUNCTYPE(None, C.POINTER(CmplxS32), C.c_int)
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libb200sdr.so (built by __graft_entry__.build()); raises if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, f32p = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_void_p
+    L.b200_init.argtypes = [i32]
+    L.b200_last_error.restype = C.c_char_p
+    L.b200_launch_count.restype = u64
+    L.b200_sm_count.restype = i32
+    L.b200_spectrum_plan_create.restype = vp
+    L.b200_spectrum_plan_create.argtypes = [i32, i32, i32, i64, i32, i32]
+    L.b200_spectrum_plan_destroy.argtypes = [vp]
+    L.b200_spectrum_plan_rows.restype = i64
+    L.b200_spectrum_plan_rows.argtypes = [vp, i64]
+    for name in ("b200_spectrum_exec", "b200_spectrum_exec_cs32", "b200_spectrum_exec_rf32"):
+        getattr(L, name).argtypes = [vp, vp, i64, i32, i64, f32p, f32p, vp, vp]
+    L.b200_fm_history_samples.argtypes = [i32]
+    L.b200_fm_history_reset.argtypes = [vp, i64, i32, i32, vp]
+    L.b200_fm_history_carry.argtypes = [vp, i64, i32, i64, i32, vp]
+    L.b200_fm_exec.argtypes = [vp, i64, i32, i64, i32, f32p, i64, vp, i64, vp]
+    L.b200_chain_exec.argtypes = [vp, i64, i32, i64, i32, f32p, f32p, i64, vp, i32, vp]
+    L.b200_session_create.restype = vp
+    L.b200_session_create.argtypes = [i32, i64]
+    L.b200_session_destroy.argtypes = [vp]
+    L.b200_session_reset.argtypes = [vp]
+    L.b200_session_chain.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.b200_host_alloc.restype = vp
+    L.b200_host_alloc.argtypes = [u64]
+    L.b200_host_free.argtypes = [vp]
+    # reference-named interface
+    L.spectrum_alloc.restype = vp
+    L.spectrum_alloc.argtypes = [i32]
+    L.spectrum_free.argtypes = [vp]
+    for name in ("spectrum_add_cmplx_u8", "spectrum_add_cmplx_s32", "spectrum_add_real_f32"):
+        getattr(L, name).argtypes = [vp, vp, vp, i32]
+    L.cic_decimate.argtypes = [i32, vp, i32, vp, i32, C.POINTER(CicDelayLine)]
+    L.halfband_decimate.restype = None
+    L.halfband_decimate.argtypes = [vp, vp, i32, vp]
+    L.rf_decimator_alloc.restype = vp
+    L.rf_decimator_add_callback.argtypes = [vp, RF_CALLBACK]
+    L.rf_decimator_set_parameters.argtypes = [vp, C.c_double, i32]
+    L.rf_decimator_decimate_cmplx_u8.argtypes = [vp, vp, i32]
+    L.rf_decimator_remove_callbacks.argtypes = [vp]
+    L.rf_decimator_free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return lib().b200_last_error().decode()
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise B200Error(f"{what} -> {rc}: {last_error()}")
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise B200Error("no CUDA device: libb200sdr has no CPU fallback")
+    return torch
+
+
+def _stream_ptr(stream=None):
+    torch = _torch()
+    s = torch.cuda.current_stream() if stream is None else stream
+    return C.c_void_p(s.cuda_stream)
+
+
+def init(device: int = 0) -> None:
+    _check(lib().b200_init(device), "b200_init")
+
+
+def launch_count() -> int:
+    return int(lib().b200_launch_count())
+
+
+# --------------------------------------------------------------------------------------
+# batched spectrum
+# --------------------------------------------------------------------------------------
+
+class SpectrumPlan:
+    """b200_spectrum_plan_*: N-point frames, K accumulated per row (spectrum.c + cbb_main.c:48-59,112-128)."""
+
+    def __init__(self, N: int = 1024, hop: int | None = None, K: int = 1, row_hop: int | None = None,
+                 window: int = WINDOW_RECT, gain_db: int = 0):
+        self.N, self.K = N, K
+        self.hop = N if hop is None else hop
+        self.row_hop = K * self.hop if row_hop is None else row_hop
+        self.h = lib().b200_spectrum_plan_create(N, self.hop, K, self.row_hop, window, gain_db)
+        if not self.h:
+            raise B200Error(f"b200_spectrum_plan_create: {last_error()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_spectrum_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def rows(self, n_samples: int) -> int:
+        return int(lib().b200_spectrum_plan_rows(self.h, n_samples))
+
+    def exec(self, iq, n_rows: int | None = None, db: bool = True, power: bool = False, db_u8: bool = False,
+             out: dict | None = None, stream=None) -> dict:
+        """iq: cuda uint8 tensor [n_streams, n_samples, 2] (rows may be strided views).
+
+        Returns a dict with the requested [n_streams, n_rows, N] tensors."""
+        torch = _torch()
+        assert iq.is_cuda and iq.dtype == torch.uint8 and iq.dim() == 3 and iq.shape[2] == 2
+        assert iq.stride(2) == 1 and iq.stride(1) == 2
+        n_streams, n_samples = iq.shape[0], iq.shape[1]
+        if n_rows is None:
+            n_rows = self.rows(n_samples)
+        res = {} if out is None else out
+        if db and "db" not in res:
+            res["db"] = torch.empty((n_streams, n_rows, self.N), dtype=torch.float32, device=iq.device)
+        if power and "power" not in res:
+            res["power"] = torch.empty((n_streams, n_rows, self.N), dtype=torch.float32, device=iq.device)
+        if db_u8 and "db_u8" not in res:
+            res["db_u8"] = torch.empty((n_streams, n_rows, self.N), dtype=torch.uint8, device=iq.device)
+        ptr = lambda k: C.c_void_p(res[k].data_ptr()) if k in res else None
+        stride = iq.stride(0) if n_streams > 1 else 0
+        _check(lib().b200_spectrum_exec(self.h, C.c_void_p(iq.data_ptr()), stride, n_streams, n_rows,
+                                        ptr("db"), ptr("power"), ptr("db_u8"), _stream_ptr(stream)),
+               "b200_spectrum_exec")
+        return res
+
+    def exec_cs32(self, x, n_rows: int | None = None, stream=None) -> dict:
+        """x: cuda int32 tensor [n_streams, n_samples, 2] (spectrum_add_cmplx_s32 semantics)."""
+        torch = _torch()
+        assert x.is_cuda and x.dtype == torch.int32 and x.is_contiguous()
+        n_streams, n_samples = x.shape[0], x.shape[1]
+        n_rows = self.rows(n_samples) if n_rows is None else n_rows
+        power = torch.empty((n_streams, n_rows, self.N), dtype=torch.float32, device=x.device)
+        _check(lib().b200_spectrum_exec_cs32(self.h, C.c_void_p(x.data_ptr()), n_samples * 8, n_streams, n_rows,
+                                             None, C.c_void_p(power.data_ptr()), None, _stream_ptr(stream)),
+               "b200_spectrum_exec_cs32")
+        return {"power": power}
+
+    def exec_rf32(self, x, n_rows: int | None = None, stream=None) -> dict:
+        """x: cuda float32 tensor [n_streams, n_samples] (spectrum_add_real_f32 semantics)."""
+        torch = _torch()
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        n_streams, n_samples = x.shape[0], x.shape[1]
+        n_rows = self.rows(n_samples) if n_rows is None else n_rows
+        power = torch.empty((n_streams, n_rows, self.N), dtype=torch.float32, device=x.device)
+        _check(lib().b200_spectrum_exec_rf32(self.h, C.c_void_p(x.data_ptr()), n_samples * 4, n_streams, n_rows,
+                                             None, C.c_void_p(power.data_ptr()), None, _stream_ptr(stream)),
+               "b200_spectrum_exec_rf32")
+        return {"power": power}
+
+
+# --------------------------------------------------------------------------------------
+# device ring of independent streams: [history | batch] per stream
+# --------------------------------------------------------------------------------------
+
+class StreamRing:
+    """Device-resident IQ of `n_streams` independent dongles laid out as the FM branch wants it:
+    each row is [history (32*R samples) | batch (n_samples)], rows 16-byte aligned."""
+
+    def __init__(self, n_streams: int, n_samples: int, R: int = 10, device="cuda"):
+        torch = _torch()
+        self.n_streams, self.n_samples, self.R = n_streams, n_samples, R
+        self.hist = int(lib().b200_fm_history_samples(R))
+        row = self.hist + n_samples
+        row = (row + 7) // 8 * 8
+        self.buf = torch.empty((n_streams, row, 2), dtype=torch.uint8, device=device)
+        self.batch = self.buf[:, self.hist:self.hist + n_samples, :]
+        self.stride_bytes = self.buf.stride(0)
+        self.reset()
+
+    def reset(self, stream=None) -> None:
+        """Every stream back to its start (history = 128: the reference's zeroed delay lines)."""
+        _check(lib().b200_fm_history_reset(C.c_void_p(self.batch.data_ptr()), self.stride_bytes, self.n_streams,
+                                           self.R, _stream_ptr(stream)), "b200_fm_history_reset")
+
+    def carry(self, stream=None) -> None:
+        """History <- tail of the batch (call after a batch has been processed)."""
+        _check(lib().b200_fm_history_carry(C.c_void_p(self.batch.data_ptr()), self.stride_bytes, self.n_streams,
+                                           self.n_samples, self.R, _stream_ptr(stream)), "b200_fm_history_carry")
+
+    def load(self, iq) -> None:
+        """Copy a [n_streams, n_samples, 2] uint8 array/tensor into the batch area."""
+        torch = _torch()
+        t = torch.as_tensor(iq)
+        self.batch.copy_(t.reshape(self.n_streams, self.n_samples, 2), non_blocking=True)
+
+
+def fm_exec(ring: StreamRing, audio=None, decimated: bool = False, stream=None):
+    """b200_fm_exec over a StreamRing -> (audio [n_streams, n/(4R)] f32, decimated [n_streams, n/R, 2] i32 | None)."""
+    torch = _torch()
+    n_audio = ring.n_samples // (4 * ring.R)
+    if audio is None:
+        audio = torch.empty((ring.n_streams, n_audio), dtype=torch.float32, device=ring.buf.device)
+    dec = None
+    if decimated:
+        dec = torch.empty((ring.n_streams, ring.n_samples // ring.R, 2), dtype=torch.int32, device=ring.buf.device)
+    _check(lib().b200_fm_exec(C.c_void_p(ring.batch.data_ptr()), ring.stride_bytes, ring.n_streams, ring.n_samples,
+                              ring.R, C.c_void_p(audio.data_ptr()), audio.stride(0),
+                              C.c_void_p(dec.data_ptr()) if dec is not None else None,
+                              dec.stride(0) // 2 if dec is not None else 0, _stream_ptr(stream)), "b200_fm_exec")
+    return audio, dec
+
+
+def chain_exec(ring: StreamRing, gain_db: int = 0, db=None, audio=None, avg_u8=None, K_avg: int = 6, stream=None):
+    """b200_chain_exec: per-frame dB spectra (N = 1024) + FM audio from one pass over the ring's batch."""
+    torch = _torch()
+    assert ring.R == 10
+    n_audio = ring.n_samples // 40
+    if db is None:
+        db = torch.empty((ring.n_streams, ring.n_samples // 1024, 1024), dtype=torch.float32, device=ring.buf.device)
+    if audio is None:
+        audio = torch.empty((ring.n_streams, n_audio), dtype=torch.float32, device=ring.buf.device)
+    _check(lib().b200_chain_exec(C.c_void_p(ring.batch.data_ptr()), ring.stride_bytes, ring.n_streams,
+                                 ring.n_samples, gain_db, C.c_void_p(db.data_ptr()), C.c_void_p(audio.data_ptr()),
+                                 audio.stride(0), C.c_void_p(avg_u8.data_ptr()) if avg_u8 is not None else None,
+                                 K_avg, _stream_ptr(stream)), "b200_chain_exec")
+    return db, audio
+
+
+class Session:
+    """b200_session_*: the host-buffer entry point (PCIe copies inside)."""
+
+    def __init__(self, n_streams: int, max_samples: int):
+        _torch()
+        self.n_streams, self.max_samples = n_streams, max_samples
+        self.h = lib().b200_session_create(n_streams, max_samples)
+        if not self.h:
+            raise B200Error(f"b200_session_create: {last_error()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_session_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def reset(self):
+        lib().b200_session_reset(self.h)
+
+    def chain(self, h_iq, n_samples: int, h_db=None, h_audio=None, gain_db: int = 0) -> None:
+        """h_iq / h_db / h_audio: host tensors or numpy arrays (pinned for asynchronous copies)."""
+        def hp(x):
+            if x is None:
+                return None
+            return C.c_void_p(x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data)
+        _check(lib().b200_session_chain(self.h, hp(h_iq), n_samples, gain_db, hp(h_db), hp(h_audio)),
+               "b200_session_chain")
+
+
+# --------------------------------------------------------------------------------------
+# the reference's interface, same names (numpy in / numpy out, synchronous)
+# --------------------------------------------------------------------------------------
+
+def spectrum_alloc(N: int):
+    h = lib().spectrum_alloc(N)
+    if not h:
+        raise B200Error(f"spectrum_alloc({N}) failed")
+    return h
+
+
+def spectrum_free(s) -> None:
+    lib().spectrum_free(s)
+
+
+def spectrum_add_cmplx_u8(s, src: np.ndarray, power_spectrum: np.ndarray, length: int) -> int:
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    assert power_spectrum.dtype == np.float64 and power_spectrum.flags.c_contiguous
+    return lib().spectrum_add_cmplx_u8(s, src.ctypes.data, power_spectrum.ctypes.data, length)
+
+
+def spectrum_add_cmplx_s32(s, src: np.ndarray, power_spectrum: np.ndarray, length: int) -> int:
+    src = np.ascontiguousarray(src, dtype=np.int32)
+    assert power_spectrum.dtype == np.float64 and power_spectrum.flags.c_contiguous
+    return lib().spectrum_add_cmplx_s32(s, src.ctypes.data, power_spectrum.ctypes.data, length)
+
+
+def spectrum_add_real_f32(s, src: np.ndarray, power_spectrum: np.ndarray, length: int) -> int:
+    src = np.ascontiguousarray(src, dtype=np.float32)
+    assert power_spectrum.dtype == np.float64 and power_spectrum.flags.c_contiguous
+    return lib().spectrum_add_real_f32(s, src.ctypes.data, power_spectrum.ctypes.data, length)
+
+
+def cic_decimate(R: int, src: np.ndarray, src_len: int, dst: np.ndarray, dst_len: int, delay: CicDelayLine) -> int:
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    assert dst.dtype == np.int32 and dst.flags.c_contiguous
+    return lib().cic_decimate(R, src.ctypes.data, src_len, dst.ctypes.data, dst_len, C.byref(delay))
+
+
+def halfband_decimate(inp: np.ndarray, out: np.ndarray, output_len: int, delay: np.ndarray) -> None:
+    inp = np.ascontiguousarray(inp, dtype=np.float32)
+    assert out.dtype == np.float32 and delay.dtype == np.float32 and len(delay) == HALF_BAND_N - 1
+    lib().halfband_decimate(inp.ctypes.data, out.ctypes.data, output_len, delay.ctypes.data)
+
+
+class RfDecimator:
+    """rf_decimator_* (rf_decimator.h:11-21): re-blocking to 100 ms, CIC on the GPU, host callbacks."""
+
+    def __init__(self):
+        self.h = lib().rf_decimator_alloc()
+        self._keep = []
+
+    def add_callback(self, fn) -> None:
+        def tramp(ptr, n):
+            arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int32)), shape=(n, 2))
+            fn(arr, n)
+        cb = RF_CALLBACK(tramp)
+        self._keep.append(cb)
+        lib().rf_decimator_add_callback(self.h, cb)
+
+    def set_parameters(self, sample_rate: float, down_factor: int) -> int:
+        return lib().rf_decimator_set_parameters(self.h, sample_rate, down_factor)
+
+    def decimate_cmplx_u8(self, signal: np.ndarray, length: int | None = None) -> int:
+        signal = np.ascontiguousarray(signal, dtype=np.uint8)
+        n = signal.size // 2 if length is None else length
+        return lib().rf_decimator_decimate_cmplx_u8(self.h, signal.ctypes.data, n)
+
+    def remove_callbacks(self) -> None:
+        lib().rf_decimator_remove_callbacks(self.h)
+        self._keep.clear()
+
+    def free(self) -> None:
+        if self.h:
+            lib().rf_decimator_free(self.h)
+            self.h = None

@@ -1,0 +1,309 @@
+// capi.cu -- the C ABI declared in include/b200sdr.h: argument checking, plans, launches.
+// Host code only; every arithmetic step happens in the kernels of this directory.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "b200_common.cuh"
+#include "fm_kernels.cuh"
+#include "spectrum_kernels.cuh"
+
+namespace b200 {
+
+std::atomic<uint64_t> g_launches{0};
+
+static thread_local char t_error[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count()
+{
+    static thread_local int cached_dev = -1;
+    static thread_local int cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+// launchers implemented next to their kernels
+int launch_spectrum1024(const SpecParams& p, cudaStream_t stream);
+int launch_spectrum_generic(const SpecParams& p, int N, int kind, cudaStream_t stream);
+int launch_fm_chain(const FmParams& p, cudaStream_t stream);
+int launch_fm_history_carry(uint8_t* iq, int64_t stride, int n_streams, int64_t n_samples, int R, cudaStream_t stream);
+int launch_fm_history_reset(uint8_t* iq, int64_t stride, int n_streams, int R, cudaStream_t stream);
+int fm_history_samples(int R);
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_spectrum_plan {
+    int N;
+    int hop;
+    int K;
+    int64_t row_hop;
+    int window;
+    int gain_db;
+    float db_offset;
+    float2* d_twiddle;
+    float* d_window;
+    int device;
+};
+
+extern "C" {
+
+int b200_init(int device)
+{
+    B200_CUDA_TRY(cudaSetDevice(device));
+    B200_CUDA_TRY(cudaFree(0));
+    cudaDeviceProp prop;
+    B200_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; libb200sdr is built for sm_100a only", device, prop.major, prop.minor);
+        return B200_ERR_CUDA;
+    }
+    return B200_OK;
+}
+
+const char* b200_last_error(void)
+{
+    return t_error;
+}
+
+uint64_t b200_launch_count(void)
+{
+    return g_launches.load(std::memory_order_relaxed);
+}
+
+int b200_sm_count(void)
+{
+    return sm_count();
+}
+
+// ---- spectrum --------------------------------------------------------------------------
+
+b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row_hop, int window, int gain_db)
+{
+    if (N < 16 || N > 65536 || (N & (N - 1)) != 0) {
+        set_error("spectrum plan: N = %d is not a power of two in [16, 65536]", N);
+        return nullptr;
+    }
+    if (hop <= 0) hop = N;
+    if (K < 1) {
+        set_error("spectrum plan: K = %d", K);
+        return nullptr;
+    }
+    if (row_hop <= 0) row_hop = (int64_t) K * hop;
+    if ((hop % 8) != 0 || (row_hop % 8) != 0) {
+        set_error("spectrum plan: hop and row_hop must be multiples of 8 samples");
+        return nullptr;
+    }
+    if (window != B200_WINDOW_RECT && window != B200_WINDOW_HANN) {
+        set_error("spectrum plan: unknown window %d", window);
+        return nullptr;
+    }
+    b200_spectrum_plan* pl = new b200_spectrum_plan();
+    pl->N = N;
+    pl->hop = hop;
+    pl->K = K;
+    pl->row_hop = row_hop;
+    pl->window = window;
+    pl->gain_db = gain_db;
+    pl->d_twiddle = nullptr;
+    pl->d_window = nullptr;
+    // cbb_main.c:112: pow(10, gain_db / 10) with the INTEGER quotient; cbb_main.c:125: / count.
+    // 2^-14 undoes the (x - 128) / 128 input scale that the kernels leave out of the transform.
+    const double g = pow(10.0, (double) (gain_db / 10));
+    pl->db_offset = (float) (10.0 * log10(g / ((double) K * 16384.0)));
+    if (cudaGetDevice(&pl->device) != cudaSuccess) {
+        set_error("spectrum plan: no CUDA device");
+        delete pl;
+        return nullptr;
+    }
+    std::vector<float2> tw((size_t) N);
+    for (int k = 0; k < N; ++k) {
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double) k / (long double) N;
+        tw[k] = make_float2((float) cosl(a), (float) sinl(a));
+    }
+    if (cudaMalloc(&pl->d_twiddle, sizeof(float2) * (size_t) N) != cudaSuccess ||
+        cudaMemcpy(pl->d_twiddle, tw.data(), sizeof(float2) * (size_t) N, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("spectrum plan: twiddle upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (pl->d_twiddle) cudaFree(pl->d_twiddle);
+        delete pl;
+        return nullptr;
+    }
+    if (window == B200_WINDOW_HANN) {
+        std::vector<float> w((size_t) N);
+        for (int i = 0; i < N; ++i)
+            w[i] = (float) (0.5L - 0.5L * cosl(2.0L * 3.14159265358979323846264338327950288L * (long double) i /
+                                               (long double) N));
+        if (cudaMalloc(&pl->d_window, sizeof(float) * (size_t) N) != cudaSuccess ||
+            cudaMemcpy(pl->d_window, w.data(), sizeof(float) * (size_t) N, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("spectrum plan: window upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            cudaFree(pl->d_twiddle);
+            if (pl->d_window) cudaFree(pl->d_window);
+            delete pl;
+            return nullptr;
+        }
+    }
+    return pl;
+}
+
+void b200_spectrum_plan_destroy(b200_spectrum_plan* plan)
+{
+    if (plan == nullptr) return;
+    if (plan->d_twiddle) cudaFree(plan->d_twiddle);
+    if (plan->d_window) cudaFree(plan->d_window);
+    delete plan;
+}
+
+// private accessors for chain.cu (not declared in the public header)
+const void* b200_spectrum_plan_twiddle_(const b200_spectrum_plan* plan) { return plan->d_twiddle; }
+float b200_spectrum_plan_db_offset_(const b200_spectrum_plan* plan) { return plan->db_offset; }
+
+int64_t b200_spectrum_plan_rows(const b200_spectrum_plan* plan, int64_t n_samples)
+{
+    const int64_t span = (int64_t) (plan->K - 1) * plan->hop + plan->N;
+    if (n_samples < span) return 0;
+    return (n_samples - span) / plan->row_hop + 1;
+}
+
+static int spectrum_exec_kind(b200_spectrum_plan* plan, const void* d_in, int64_t stream_stride_bytes, int n_streams,
+                              int64_t n_rows, float* d_db, float* d_power, uint8_t* d_db_u8, int kind,
+                              void* cuda_stream)
+{
+    if (plan == nullptr || n_streams < 0 || n_rows < 0) {
+        set_error("spectrum exec: bad arguments");
+        return B200_ERR_ARG;
+    }
+    if (n_streams == 0 || n_rows == 0) return B200_OK;
+    if (d_in == nullptr) {
+        set_error("spectrum exec: null input");
+        return B200_ERR_ARG;
+    }
+    SpecParams p;
+    p.iq = reinterpret_cast<const uint8_t*>(d_in);
+    p.stream_stride_bytes = stream_stride_bytes;
+    p.n_streams = n_streams;
+    p.n_rows = n_rows;
+    p.hop = plan->hop;
+    p.K = plan->K;
+    p.row_hop = plan->row_hop;
+    p.db = d_db;
+    p.power = d_power;
+    p.db_u8 = d_db_u8;
+    p.db_offset = plan->db_offset;
+    p.twiddle = plan->d_twiddle;
+    p.window = plan->d_window;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if (kind == 0 && plan->N == 1024) {
+        if ((reinterpret_cast<uintptr_t>(d_in) & 15) != 0 || (stream_stride_bytes & 15) != 0) {
+            set_error("spectrum exec: IQ pointer and stream stride must be 16-byte aligned");
+            return B200_ERR_ALIGN;
+        }
+        return launch_spectrum1024(p, stream);
+    }
+    return launch_spectrum_generic(p, plan->N, kind, stream);
+}
+
+int b200_spectrum_exec(b200_spectrum_plan* plan, const uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams,
+                       int64_t n_rows, float* d_db, float* d_power, uint8_t* d_db_u8, void* cuda_stream)
+{
+    return spectrum_exec_kind(plan, d_iq, stream_stride_bytes, n_streams, n_rows, d_db, d_power, d_db_u8, 0,
+                              cuda_stream);
+}
+
+int b200_spectrum_exec_cs32(b200_spectrum_plan* plan, const int32_t* d_iq, int64_t stream_stride_bytes, int n_streams,
+                            int64_t n_rows, float* d_db, float* d_power, uint8_t* d_db_u8, void* cuda_stream)
+{
+    return spectrum_exec_kind(plan, d_iq, stream_stride_bytes, n_streams, n_rows, d_db, d_power, d_db_u8, 1,
+                              cuda_stream);
+}
+
+int b200_spectrum_exec_rf32(b200_spectrum_plan* plan, const float* d_x, int64_t stream_stride_bytes, int n_streams,
+                            int64_t n_rows, float* d_db, float* d_power, uint8_t* d_db_u8, void* cuda_stream)
+{
+    return spectrum_exec_kind(plan, d_x, stream_stride_bytes, n_streams, n_rows, d_db, d_power, d_db_u8, 2,
+                              cuda_stream);
+}
+
+// ---- FM branch ---------------------------------------------------------------------------
+
+int b200_fm_history_samples(int R)
+{
+    return fm_history_samples(R);
+}
+
+int b200_fm_history_reset(uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams, int R, void* cuda_stream)
+{
+    if (d_iq == nullptr || R < 1 || R > 256 || n_streams < 0) {
+        set_error("fm history reset: bad arguments");
+        return B200_ERR_ARG;
+    }
+    return launch_fm_history_reset(d_iq, stream_stride_bytes, n_streams, R, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int b200_fm_history_carry(uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams, int64_t n_samples, int R,
+                          void* cuda_stream)
+{
+    if (d_iq == nullptr || R < 1 || R > 256 || n_streams < 0) {
+        set_error("fm history carry: bad arguments");
+        return B200_ERR_ARG;
+    }
+    return launch_fm_history_carry(d_iq, stream_stride_bytes, n_streams, n_samples, R,
+                                   reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int b200_fm_exec(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams, int64_t n_samples, int R,
+                 float* d_audio, int64_t audio_stride, int32_t* d_decimated, int64_t dec_stride, void* cuda_stream)
+{
+    if (d_iq == nullptr || d_audio == nullptr || n_streams < 0) {
+        set_error("fm exec: bad arguments");
+        return B200_ERR_ARG;
+    }
+    FmParams p;
+    p.iq = d_iq;
+    p.stream_stride_bytes = stream_stride_bytes;
+    p.n_streams = n_streams;
+    p.n_samples = n_samples;
+    p.R = R;
+    p.audio = d_audio;
+    p.audio_stride = audio_stride;
+    p.decimated = d_decimated;
+    p.dec_stride = dec_stride;
+    return launch_fm_chain(p, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+// ---- pinned host memory --------------------------------------------------------------------
+
+void* b200_host_alloc(uint64_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, (size_t) bytes, cudaHostAllocDefault) != cudaSuccess) {
+        set_error("b200_host_alloc(%llu): %s", (unsigned long long) bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+
+void b200_host_free(void* p)
+{
+    if (p != nullptr) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// chain.cu -- the full spectrum + FM chain entry points (b200sdr.h): device-resident
+// b200_chain_exec and the host-buffer session that wraps it with pipelined PCIe copies.
+#include <mutex>
+#include <map>
+
+#include "b200_common.cuh"
+#include "fm_kernels.cuh"
+#include "spectrum_kernels.cuh"
+
+namespace b200 {
+int launch_chain_fused(const uint8_t* d_iq, int64_t stride, int n_streams, int64_t n_samples, float db_offset,
+                       const float2* twiddle, float* d_db, float* d_audio, int64_t audio_stride, cudaStream_t stream);
+int launch_fm_history_carry(uint8_t* iq, int64_t stride, int n_streams, int64_t n_samples, int R, cudaStream_t stream);
+int launch_fm_history_reset(uint8_t* iq, int64_t stride, int n_streams, int R, cudaStream_t stream);
+int fm_history_samples(int R);
+}  // namespace b200
+
+using namespace b200;
+
+namespace {
+
+constexpr int CHAIN_N = 1024;      // cbb_main.c:17 FFT_POINTS
+constexpr int CHAIN_R = 10;        // cbb_main.c:80 at rtl_sensor.c:12's 2.048 MS/s and main.c:23's 192 kHz
+constexpr int CHAIN_TILE = 5120;   // lcm(1024, 4 * R): 5 frames = 128 audio samples
+
+std::mutex g_plan_mutex;
+// (device, K, gain_db) -> plan; plans are tiny (a twiddle table) and live for the process
+std::map<std::tuple<int, int, int>, b200_spectrum_plan*> g_plans;
+
+b200_spectrum_plan* cached_plan(int K, int gain_db)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    auto key = std::make_tuple(dev, K, gain_db);
+    auto it = g_plans.find(key);
+    if (it != g_plans.end()) return it->second;
+    b200_spectrum_plan* pl = b200_spectrum_plan_create(CHAIN_N, CHAIN_N, K, 0, B200_WINDOW_RECT, gain_db);
+    if (pl != nullptr) g_plans[key] = pl;
+    return pl;
+}
+
+}  // namespace
+
+// layout of b200_spectrum_plan is private to capi.cu; the fused launcher needs two fields
+extern "C" const void* b200_spectrum_plan_twiddle_(const b200_spectrum_plan* plan);
+extern "C" float b200_spectrum_plan_db_offset_(const b200_spectrum_plan* plan);
+
+extern "C" {
+
+int b200_chain_exec(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams, int64_t n_samples, int gain_db,
+                    float* d_db, float* d_audio, int64_t audio_stride, uint8_t* d_avg_u8, int K_avg,
+                    void* cuda_stream)
+{
+    if (d_iq == nullptr || n_streams < 0 || n_samples < 0 || n_samples % CHAIN_TILE != 0) {
+        set_error("chain exec: n_samples %lld must be a non-negative multiple of %d", (long long) n_samples, CHAIN_TILE);
+        return B200_ERR_ARG;
+    }
+    if ((reinterpret_cast<uintptr_t>(d_iq) & 15) != 0 || (stream_stride_bytes & 15) != 0) {
+        set_error("chain exec: IQ pointer and stream stride must be 16-byte aligned");
+        return B200_ERR_ALIGN;
+    }
+    if (n_streams == 0 || n_samples == 0) return B200_OK;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    b200_spectrum_plan* pl = cached_plan(1, gain_db);
+    if (pl == nullptr) return B200_ERR_CUDA;
+
+    int rc;
+    if (d_db != nullptr && d_audio != nullptr) {
+        rc = launch_chain_fused(d_iq, stream_stride_bytes, n_streams, n_samples, b200_spectrum_plan_db_offset_(pl),
+                                reinterpret_cast<const float2*>(b200_spectrum_plan_twiddle_(pl)), d_db, d_audio,
+                                audio_stride, stream);
+        if (rc) return rc;
+    } else {
+        if (d_db != nullptr) {
+            rc = b200_spectrum_exec(pl, d_iq, stream_stride_bytes, n_streams, n_samples / CHAIN_N, d_db, nullptr,
+                                    nullptr, cuda_stream);
+            if (rc) return rc;
+        }
+        if (d_audio != nullptr) {
+            rc = b200_fm_exec(d_iq, stream_stride_bytes, n_streams, n_samples, CHAIN_R, d_audio, audio_stride, nullptr,
+                              0, cuda_stream);
+            if (rc) return rc;
+        }
+    }
+    if (d_avg_u8 != nullptr) {
+        if (K_avg < 1 || (int64_t) K_avg * CHAIN_N > n_samples) {
+            set_error("chain exec: K_avg = %d does not fit the batch", K_avg);
+            return B200_ERR_ARG;
+        }
+        b200_spectrum_plan* avg = cached_plan(K_avg, gain_db);
+        if (avg == nullptr) return B200_ERR_CUDA;
+        rc = b200_spectrum_exec(avg, d_iq, stream_stride_bytes, n_streams, 1, nullptr, nullptr, d_avg_u8, cuda_stream);
+        if (rc) return rc;
+    }
+    return B200_OK;
+}
+
+}  // extern "C"
+
+// ---- host-buffer session -----------------------------------------------------------------
+
+struct b200_session {
+    int n_streams;
+    int64_t max_samples;
+    int hist_samples;
+    int64_t stride_bytes;      // per-stream row pitch in the device ring: history + batch
+    uint8_t* d_ring;           // [n_streams][stride_bytes]
+    float* d_db;               // [n_streams][max_samples]            (1024 bins per 1024 samples)
+    float* d_audio;            // [n_streams][max_samples / 40]
+    static constexpr int LANES = 4;
+    cudaStream_t streams[LANES];
+    int device;
+};
+
+extern "C" {
+
+b200_session* b200_session_create(int n_streams, int64_t max_samples_per_batch)
+{
+    if (n_streams < 1 || max_samples_per_batch < CHAIN_TILE || max_samples_per_batch % CHAIN_TILE != 0) {
+        set_error("session: max_samples_per_batch must be a positive multiple of %d", CHAIN_TILE);
+        return nullptr;
+    }
+    b200_session* s = new b200_session();
+    memset(s, 0, sizeof(*s));
+    s->n_streams = n_streams;
+    s->max_samples = max_samples_per_batch;
+    s->hist_samples = fm_history_samples(CHAIN_R);
+    s->stride_bytes = 2 * ((int64_t) s->hist_samples + max_samples_per_batch);
+    bool ok = cudaGetDevice(&s->device) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_ring, (size_t) n_streams * (size_t) s->stride_bytes) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_db, sizeof(float) * (size_t) n_streams * (size_t) max_samples_per_batch) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_audio, sizeof(float) * (size_t) n_streams * (size_t) (max_samples_per_batch / 40)) ==
+                   cudaSuccess;
+    for (int i = 0; ok && i < b200_session::LANES; ++i)
+        ok = cudaStreamCreateWithFlags(&s->streams[i], cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {
+        set_error("session: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        b200_session_destroy(s);
+        return nullptr;
+    }
+    b200_session_reset(s);
+    return s;
+}
+
+void b200_session_destroy(b200_session* s)
+{
+    if (s == nullptr) return;
+    for (int i = 0; i < b200_session::LANES; ++i)
+        if (s->streams[i]) cudaStreamDestroy(s->streams[i]);
+    if (s->d_ring) cudaFree(s->d_ring);
+    if (s->d_db) cudaFree(s->d_db);
+    if (s->d_audio) cudaFree(s->d_audio);
+    delete s;
+}
+
+void b200_session_reset(b200_session* s)
+{
+    if (s == nullptr) return;
+    launch_fm_history_reset(s->d_ring + 2 * (int64_t) s->hist_samples, s->stride_bytes, s->n_streams, CHAIN_R,
+                            s->streams[0]);
+    cudaStreamSynchronize(s->streams[0]);
+}
+
+int b200_session_chain(b200_session* s, const uint8_t* h_iq, int64_t n_samples, int gain_db, float* h_db,
+                       float* h_audio)
+{
+    if (s == nullptr || h_iq == nullptr || n_samples < 0 || n_samples > s->max_samples || n_samples % CHAIN_TILE != 0) {
+        set_error("session chain: n_samples %lld must be a multiple of %d and at most %lld", (long long) n_samples,
+                  CHAIN_TILE, s ? (long long) s->max_samples : 0ll);
+        return B200_ERR_ARG;
+    }
+    if (n_samples == 0) return B200_OK;
+    const int lanes = b200_session::LANES;
+    // stream groups small enough to pipeline H2D / kernels / D2H across the lanes
+    int group = (s->n_streams + 4 * lanes - 1) / (4 * lanes);
+    if (group < 1) group = 1;
+    const int64_t n_audio = n_samples / 40;
+    int lane = 0;
+    for (int s0 = 0; s0 < s->n_streams; s0 += group, lane = (lane + 1) % lanes) {
+        const int ns = (s->n_streams - s0) < group ? (s->n_streams - s0) : group;
+        cudaStream_t st = s->streams[lane];
+        uint8_t* d_batch = s->d_ring + (int64_t) s0 * s->stride_bytes + 2 * (int64_t) s->hist_samples;
+        float* d_db = s->d_db + (size_t) s0 * (size_t) n_samples;
+        float* d_audio = s->d_audio + (size_t) s0 * (size_t) n_audio;
+        B200_CUDA_TRY(cudaMemcpy2DAsync(d_batch, (size_t) s->stride_bytes, h_iq + (size_t) s0 * 2 * (size_t) n_samples,
+                                        (size_t) (2 * n_samples), (size_t) (2 * n_samples), (size_t) ns,
+                                        cudaMemcpyHostToDevice, st));
+        const int rc = b200_chain_exec(d_batch, s->stride_bytes, ns, n_samples, gain_db, h_db ? d_db : nullptr,
+                                       h_audio ? d_audio : nullptr, n_audio, nullptr, 0, st);
+        if (rc) return rc;
+        if (h_db)
+            B200_CUDA_TRY(cudaMemcpyAsync(h_db + (size_t) s0 * (size_t) n_samples, d_db,
+                                          sizeof(float) * (size_t) ns * (size_t) n_samples, cudaMemcpyDeviceToHost, st));
+        if (h_audio)
+            B200_CUDA_TRY(cudaMemcpyAsync(h_audio + (size_t) s0 * (size_t) n_audio, d_audio,
+                                          sizeof(float) * (size_t) ns * (size_t) n_audio, cudaMemcpyDeviceToHost, st));
+        const int rc2 = launch_fm_history_carry(d_batch, s->stride_bytes, ns, n_samples, CHAIN_R, st);
+        if (rc2) return rc2;
+    }
+    for (int i = 0; i < lanes; ++i) B200_CUDA_TRY(cudaStreamSynchronize(s->streams[i]));
+    return B200_OK;
+}
+
+}  // extern "C"

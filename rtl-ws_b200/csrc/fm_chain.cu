@@ -1,0 +1,260 @@
+// fm_chain.cu -- the FM branch as ONE pass over the IQ bytes (sm_100a):
+//   u8 IQ --CIC(R)--> int32 --atan2_approx--> phase --diff + limiter--> demod
+//         --half-band /2--> --half-band /2--> float audio          (one float per 4R samples)
+//
+// Reference arithmetic (paths relative to the reference's src/): resample.c:6-45,
+// common_sp.h:40-76, audio_main.c:110-139, resample.c:47-67.  The reference carries state
+// in delay structs between 100 ms blocks; here every output is computed from its full
+// dependency cone of INPUT samples instead -- audio[n] needs decimated samples 4n-31..4n,
+// i.e. 32*R input samples of history -- so tiles are independent and the only state a
+// stream carries between batches is its last 32*R input bytes pairs (b200sdr.h).
+//
+// A CTA walks tiles of T audio samples.  The tile's bytes ((4T + 32) * 2R, 10880 at
+// R = 10) are staged by the TMA unit into a two-deep shared ring; phases:
+//   1. one thread per decimated sample: byte sums with dp4a, atan2_approx -> phase[] (smem)
+//   2. one thread per first-stage output: diff, limiter, half-band -> work[] (smem)
+//   3. one thread per audio sample: half-band -> global
+#include "b200_common.cuh"
+#include "fm_kernels.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int FM_THREADS = 256;
+
+__host__ __device__ inline int fm_tile_audio(int R)
+{
+    int T = 128;
+    while (T > 8 && (4 * T + 32) * 2 * R > 32768) T >>= 1;
+    return T;
+}
+
+// RT = 10: the default decimation (cbb_main.c:80), word loads + dp4a, fully unrolled.
+// RT = 0:  any R, sample-wise.
+template <int RT>
+__global__ void __launch_bounds__(FM_THREADS) fm_chain_kernel(const FmParams p, const int T, const int tiles_per_stream,
+                                                              const int stage_bytes)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int R = RT ? RT : p.R;
+    const int tid = threadIdx.x;
+    uint8_t* ring = smem;
+    float* phase = reinterpret_cast<float*>(smem + 2 * stage_bytes);
+    float* work = phase + (4 * T + 32);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(work + (2 * T + 16));
+
+    const int64_t n_audio = p.n_samples / (4 * R);
+    const int64_t total_tiles = (int64_t) p.n_streams * tiles_per_stream;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t tile, int st) {
+        const int s = (int) (tile / tiles_per_stream);
+        const int64_t n0 = (int64_t) (tile - (int64_t) s * tiles_per_stream) * T;
+        const int ta = (int) ((n_audio - n0) < T ? (n_audio - n0) : T);
+        const uint32_t bytes = (uint32_t) (4 * ta + 32) * 2u * (uint32_t) R;
+        const uint8_t* src = p.iq + (int64_t) s * p.stream_stride_bytes + (4 * n0 - 32) * 2 * (int64_t) R;
+        mbar_arrive_expect_tx(&bars[st], bytes);
+        tma_load_1d(ring + st * stage_bytes, src, bytes, &bars[st]);
+    };
+
+    int64_t tile = blockIdx.x;
+    if (tid == 0) {
+        if (tile < total_tiles) issue(tile, 0);
+        if (tile + gridDim.x < total_tiles) issue(tile + gridDim.x, 1);
+    }
+
+    for (uint32_t it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        const int s = (int) (tile / tiles_per_stream);
+        const int64_t n0 = (int64_t) (tile - (int64_t) s * tiles_per_stream) * T;
+        const int ta = (int) ((n_audio - n0) < T ? (n_audio - n0) : T);
+        const int nd = 4 * ta + 32;       // decimated samples in this tile, local index 0 <-> 4*n0 - 32
+
+        mbar_wait(&bars[st], (it >> 1) & 1);
+        const uint8_t* in = ring + st * stage_bytes;
+
+        // ---- phase 1: CIC boxcar (resample.c:21-40) + atan2_approx ----
+        for (int j = tid; j < nd; j += FM_THREADS) {
+            int sre, sim;
+            if (RT == 10) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(in + j * 20);
+                uint32_t ure = 0, uim = 0;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const uint32_t v = w[k];
+                    ure = __dp4a(v, 0x00010001u, ure);
+                    uim = __dp4a(v, 0x01000100u, uim);
+                }
+                sre = (int) ure - 1280;
+                sim = (int) uim - 1280;
+            } else {
+                const uint16_t* h = reinterpret_cast<const uint16_t*>(in) + (size_t) j * R;
+                uint32_t ure = 0, uim = 0;
+                for (int k = 0; k < R; ++k) {
+                    const uint32_t v = h[k];
+                    ure += v & 0xffu;
+                    uim += v >> 8;
+                }
+                sre = (int) ure - 128 * R;
+                sim = (int) uim - 128 * R;
+            }
+            phase[j] = atan2_approx_dev(sim, sre);
+            if (p.decimated != nullptr && j >= 32) {
+                int2* dst = reinterpret_cast<int2*>(p.decimated) + (int64_t) s * p.dec_stride + (4 * n0 + (j - 32));
+                *dst = make_int2(sre, sim);
+            }
+        }
+        __syncthreads();
+        // the input stage is consumed: refill it with the tile two steps ahead
+        if (tid == 0) {
+            const int64_t nxt = tile + 2 * (int64_t) gridDim.x;
+            if (nxt < total_tiles) {
+                fence_proxy_async_smem();
+                issue(nxt, st);
+            }
+        }
+
+        // ---- phase 2: discriminator + limiter (audio_main.c:110-131), half-band #1 ----
+        const int nw = 2 * ta + 10;        // work index 0 <-> 2*n0 - 10
+        for (int m = tid; m < nw; m += FM_THREADS) {
+            const int j = 2 * m + 12;      // demod index feeding tap k = 0
+            float ph[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) ph[k] = phase[j - k];
+            // d(k) = limit(phase[j-k] - phase[j-k-1])
+            const float d0 = fm_limit(ph[0], ph[1]);
+            const float d2 = fm_limit(ph[2], ph[3]);
+            const float d4 = fm_limit(ph[4], ph[5]);
+            const float d5 = fm_limit(ph[5], ph[6]);
+            const float d6 = fm_limit(ph[6], ph[7]);
+            const float d8 = fm_limit(ph[8], ph[9]);
+            const float d10 = fm_limit(ph[10], ph[11]);
+            work[m] = halfband_taps(d0, d2, d4, d5, d6, d8, d10);
+        }
+        __syncthreads();
+
+        // ---- phase 3: half-band #2 (audio_main.c:139) ----
+        for (int a = tid; a < ta; a += FM_THREADS) {
+            const int m = 2 * a + 10;
+            const float v = halfband_taps(work[m], work[m - 2], work[m - 4], work[m - 5], work[m - 6], work[m - 8],
+                                          work[m - 10]);
+            p.audio[(int64_t) s * p.audio_stride + n0 + a] = v;
+        }
+        // phase[] / work[] are rewritten only after the next tile's barriers; the next
+        // iteration's phase-1 writes to phase[] cannot overtake phase-2 reads because of the
+        // __syncthreads above, and its phase-2 writes to work[] come after its own first
+        // __syncthreads, which every phase-3 reader of this tile has to reach first.
+    }
+}
+
+// history <- last H samples of the batch (per stream); H*2 bytes, 16-byte granules
+__global__ void fm_history_carry_kernel(uint8_t* iq, int64_t stride, int n_streams, int64_t n_bytes, int hist_bytes)
+{
+    const int granules = hist_bytes / 16;
+    const int64_t total = (int64_t) n_streams * granules;
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x) {
+        const int s = (int) (i / granules);
+        const int g = (int) (i - (int64_t) s * granules);
+        uint8_t* base = iq + (int64_t) s * stride;
+        const uint4 v = *reinterpret_cast<const uint4*>(base + n_bytes - hist_bytes + 16 * g);
+        *reinterpret_cast<uint4*>(base - hist_bytes + 16 * g) = v;
+    }
+}
+
+__global__ void fm_history_reset_kernel(uint8_t* iq, int64_t stride, int n_streams, int hist_bytes)
+{
+    const int granules = hist_bytes / 16;
+    const int64_t total = (int64_t) n_streams * granules;
+    const uint4 v = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x) {
+        const int s = (int) (i / granules);
+        const int g = (int) (i - (int64_t) s * granules);
+        *reinterpret_cast<uint4*>(iq + (int64_t) s * stride - hist_bytes + 16 * g) = v;
+    }
+}
+
+}  // namespace
+
+int fm_history_samples(int R)
+{
+    return 32 * R;
+}
+
+int launch_fm_chain(const FmParams& p, cudaStream_t stream)
+{
+    if (p.R < 1 || p.R > 256) {
+        set_error("fm: down factor %d outside [1, 256]", p.R);
+        return B200_ERR_ARG;
+    }
+    if (p.n_samples < 0 || p.n_samples % (4 * p.R) != 0 || p.n_samples % 8 != 0) {
+        set_error("fm: n_samples %lld must be a multiple of 4*R and of 8", (long long) p.n_samples);
+        return B200_ERR_ARG;
+    }
+    if ((reinterpret_cast<uintptr_t>(p.iq) & 15) != 0 || (p.stream_stride_bytes & 15) != 0) {
+        set_error("fm: IQ pointer and stream stride must be 16-byte aligned");
+        return B200_ERR_ALIGN;
+    }
+    if (p.n_streams == 0 || p.n_samples == 0) return B200_OK;
+    const int T = fm_tile_audio(p.R);
+    const int64_t n_audio = p.n_samples / (4 * p.R);
+    const int64_t tiles_per_stream = (n_audio + T - 1) / T;
+    if (tiles_per_stream >= (1ll << 31)) {
+        set_error("fm: batch too long");
+        return B200_ERR_ARG;
+    }
+    const int stage_bytes = (4 * T + 32) * 2 * p.R;
+    const int smem = 2 * stage_bytes + (4 * T + 32) * 4 + (2 * T + 16) * 4 + 16;
+    auto kern = (p.R == 10) ? fm_chain_kernel<10> : fm_chain_kernel<0>;
+    static bool configured[2] = {false, false};
+    if (!configured[p.R == 10]) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32768 + 8192));
+        configured[p.R == 10] = true;
+    }
+    int ctas_per_sm = 0;
+    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, FM_THREADS, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    int64_t grid = (int64_t) sm_count() * ctas_per_sm;
+    const int64_t total_tiles = (int64_t) p.n_streams * tiles_per_stream;
+    if (grid > total_tiles) grid = total_tiles;
+    kern<<<(unsigned) grid, FM_THREADS, smem, stream>>>(p, T, (int) tiles_per_stream, stage_bytes);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+int launch_fm_history_carry(uint8_t* iq, int64_t stride, int n_streams, int64_t n_samples, int R, cudaStream_t stream)
+{
+    const int hist_bytes = 2 * fm_history_samples(R);
+    if (n_samples * 2 < hist_bytes) {
+        set_error("fm: batch shorter than the history (%d samples)", fm_history_samples(R));
+        return B200_ERR_ARG;
+    }
+    if ((reinterpret_cast<uintptr_t>(iq) & 15) != 0 || (stride & 15) != 0 || ((n_samples * 2) & 15) != 0)
+        return B200_ERR_ALIGN;
+    if (n_streams == 0) return B200_OK;
+    const int64_t total = (int64_t) n_streams * (hist_bytes / 16);
+    const int blocks = (int) ((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    fm_history_carry_kernel<<<blocks, 256, 0, stream>>>(iq, stride, n_streams, n_samples * 2, hist_bytes);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+int launch_fm_history_reset(uint8_t* iq, int64_t stride, int n_streams, int R, cudaStream_t stream)
+{
+    const int hist_bytes = 2 * fm_history_samples(R);
+    if ((reinterpret_cast<uintptr_t>(iq) & 15) != 0 || (stride & 15) != 0) return B200_ERR_ALIGN;
+    if (n_streams == 0) return B200_OK;
+    const int64_t total = (int64_t) n_streams * (hist_bytes / 16);
+    const int blocks = (int) ((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    fm_history_reset_kernel<<<blocks, 256, 0, stream>>>(iq, stride, n_streams, hist_bytes);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,245 @@
+// spectrum1024.cu -- batched 1024-point power spectra, one warp per frame (sm_100a).
+//
+// Reference arithmetic reproduced per frame (paths relative to the reference's src/):
+//   spectrum.c:54-58   unpack  in = (u8 - 128) / 128                (the /128 is folded into
+//                                                                   the power scale: exact)
+//   spectrum.c:21      unnormalised forward DFT (FFTW_FORWARD)
+//   spectrum.c:23-34   out[i] += |X[(i + N/2) mod N]|^2, and out[N/2] += out[N/2 - 1]
+//   cbb_main.c:125-128 10*log10(|g * P / K|), (int) truncation, clamp to [0, 255]
+//
+// Decomposition 1024 = 32 x 32 with n = 32*n1 + n2, k = k1 + 32*k2:
+//   pass 1: lane n2 holds x[32*n1 + n2] (n1 = 0..31) in registers, 32-point FFT over n1,
+//           multiply by W_1024^(n2*k1) (lane-private twiddles kept in registers for the
+//           life of the persistent warp), write row k1 of a padded shared tile;
+//   pass 2: lane k1 reads its row (all n2), 32-point FFT over n2 -> bins k1 + 32*k2.
+// One shared-memory exchange per frame, warp-private: no block-level barrier anywhere.
+// A warp store for fixed k2 covers 32 consecutive bins = 128 contiguous bytes.
+//
+// Input frames are staged by the TMA unit (cp.async.bulk, 2 KB per frame) into a
+// warp-private two-deep ring guarded by mbarriers, so the next frame streams in from HBM
+// while the current one is in the butterflies.
+#include "b200_common.cuh"
+#include "fft_regs.cuh"
+#include "spectrum_kernels.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int N1024 = 1024;
+constexpr int FRAME_BYTES = 2 * N1024;             // u8 re + u8 im
+constexpr int XCH_STRIDE = 34;                     // float2 per row; 34 keeps LDS.128 and STS.64 conflict-free
+constexpr int XCH_BYTES = 32 * XCH_STRIDE * 8;     // 8704
+constexpr int WARP_SMEM = 2 * FRAME_BYTES + XCH_BYTES + 32;   // ring + exchange tile + 2 mbarriers (padded)
+constexpr int WARPS_PER_CTA = 4;
+constexpr int CTA_SMEM = WARPS_PER_CTA * WARP_SMEM + N1024 * 4;   // + window copy
+
+__device__ __forceinline__ const uint8_t* frame_src(const SpecParams& p, uint32_t item, int j)
+{
+    // item = stream * n_rows + row; 32-bit division: total items < 2^31 is enforced by the launcher
+    const uint32_t n_rows = (uint32_t) p.n_rows;
+    const uint32_t s = item / n_rows;
+    const uint32_t r = item - s * n_rows;
+    return p.iq + (int64_t) s * p.stream_stride_bytes + 2 * ((int64_t) r * p.row_hop + (int64_t) j * p.hop);
+}
+
+template <bool MULTI, bool WINDOW>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) spectrum1024_kernel(const SpecParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint8_t* wbase = smem + warp * WARP_SMEM;
+    uint8_t* ring = wbase;
+    float2* xch = reinterpret_cast<float2*>(wbase + 2 * FRAME_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + 2 * FRAME_BYTES + XCH_BYTES);
+    float* win = reinterpret_cast<float*>(smem + WARPS_PER_CTA * WARP_SMEM);
+
+    if (WINDOW) {
+        for (int i = threadIdx.x; i < N1024; i += blockDim.x) win[i] = p.window[i];
+        __syncthreads();
+    }
+
+    const uint32_t total_items = (uint32_t) p.n_streams * (uint32_t) p.n_rows;
+    const uint32_t gw = blockIdx.x * WARPS_PER_CTA + warp;
+    const uint32_t GW = gridDim.x * WARPS_PER_CTA;
+    if (gw >= total_items) return;
+    const uint32_t n_items = (total_items - gw + GW - 1) / GW;
+    const int K = MULTI ? p.K : 1;
+
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    // lane-private inter-pass twiddles W_1024^(lane * k1)
+    float2 tw[32];
+#pragma unroll
+    for (int k1 = 1; k1 < 32; ++k1) tw[k1] = __ldg(&p.twiddle[(lane * k1) & (N1024 - 1)]);
+
+    // producer cursor (lane 0 only cares)
+    uint32_t ld_item = gw;
+    int ld_j = 0;
+    uint32_t ld_left = n_items * (uint32_t) K;   // frames not yet requested
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+            if (ld_left > 0) {
+                mbar_arrive_expect_tx(&bars[st], FRAME_BYTES);
+                tma_load_1d(ring + st * FRAME_BYTES, frame_src(p, ld_item, ld_j), FRAME_BYTES, &bars[st]);
+                --ld_left;
+                if (++ld_j == K) { ld_j = 0; ld_item += GW; }
+            }
+        }
+    }
+
+    float acc[32];
+    float dcacc = 0.0f;
+    if (MULTI) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) acc[q] = 0.0f;
+    }
+
+    uint32_t f = 0;
+    for (uint32_t it = 0; it < n_items; ++it) {
+        const uint32_t item = gw + it * GW;
+        for (int j = 0; j < K; ++j, ++f) {
+            const int st = f & 1;
+            mbar_wait(&bars[st], (f >> 1) & 1);
+
+            // ---- unpack: byte -> float via the 2^23 magic constant (exact), minus 128 ----
+            float2 a[32];
+            const uint16_t* in16 = reinterpret_cast<const uint16_t*>(ring + st * FRAME_BYTES);
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const uint32_t v = in16[32 * n1 + lane];
+                a[n1].x = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540)) - 8388736.0f;
+                a[n1].y = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7541)) - 8388736.0f;
+                if (WINDOW) {
+                    const float w = win[32 * n1 + lane];
+                    a[n1].x *= w;
+                    a[n1].y *= w;
+                }
+            }
+            __syncwarp();
+            // stage `st` is free again: request the frame two ahead
+            if (lane == 0 && ld_left > 0) {
+                fence_proxy_async_smem();
+                mbar_arrive_expect_tx(&bars[st], FRAME_BYTES);
+                tma_load_1d(ring + st * FRAME_BYTES, frame_src(p, ld_item, ld_j), FRAME_BYTES, &bars[st]);
+                --ld_left;
+                if (++ld_j == K) { ld_j = 0; ld_item += GW; }
+            }
+
+            // ---- pass 1: FFT over n1, twiddle, transpose through shared ----
+            fft_dif<32>(a);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int k1 = bitrev<32>(q);
+                const float2 v = (k1 == 0) ? a[q] : cmul(a[q], tw[k1]);
+                xch[k1 * XCH_STRIDE + lane] = v;
+            }
+            __syncwarp();
+            float2 b[32];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const float4 v = *reinterpret_cast<const float4*>(&xch[lane * XCH_STRIDE + 2 * m]);
+                b[2 * m] = make_float2(v.x, v.y);
+                b[2 * m + 1] = make_float2(v.z, v.w);
+            }
+            // (the next frame's __syncwarp after its unpack orders these reads before its writes)
+
+            // ---- pass 2: FFT over n2 -> bins lane + 32 * bitrev(q) ----
+            fft_dif<32>(b);
+
+            if (!MULTI) {
+                float pw[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) pw[q] = fmaf(b[q].x, b[q].x, b[q].y * b[q].y);
+                // DC-position patch (spectrum.c:30-33): display index N/2 (bin 0: lane 0, q 0)
+                // takes the value of display index N/2-1 (bin 1023: lane 31, q 31)
+                const float left = __shfl_sync(0xffffffffu, pw[31], 31);
+                if (lane == 0) pw[0] = left;
+                const size_t row = (size_t) item * N1024;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int k2 = bitrev<32>(q);
+                    const int col = lane + 32 * ((k2 + 16) & 31);     // fftshift
+                    const float db = fmaf(3.01029995663981195f, __log2f(pw[q]), p.db_offset);
+                    if (p.db) st_stream_f32(p.db + row + col, db);
+                    if (p.power) st_stream_f32(p.power + row + col, pw[q] * (1.0f / 16384.0f));
+                    if (p.db_u8) {
+                        int m = __float2int_rz(db);
+                        m = m < 0 ? 0 : (m > 255 ? 255 : m);
+                        p.db_u8[row + col] = (uint8_t) m;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const float pw = fmaf(b[q].x, b[q].x, b[q].y * b[q].y);
+                    acc[q] += pw;
+                    // cumulative DC patch: after K adds the DC position holds
+                    // sum_j (K - j) * |X_j[N-1]|^2, j = 0..K-1
+                    if (q == 31) dcacc = fmaf((float) (K - j), pw, dcacc);
+                }
+            }
+        }
+        if (MULTI) {
+            const float left = __shfl_sync(0xffffffffu, dcacc, 31);
+            if (lane == 0) acc[0] = left;
+            const size_t row = (size_t) item * N1024;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int k2 = bitrev<32>(q);
+                const int col = lane + 32 * ((k2 + 16) & 31);
+                const float db = fmaf(3.01029995663981195f, __log2f(acc[q]), p.db_offset);
+                if (p.db) st_stream_f32(p.db + row + col, db);
+                if (p.power) st_stream_f32(p.power + row + col, acc[q] * (1.0f / 16384.0f));
+                if (p.db_u8) {
+                    int m = __float2int_rz(db);
+                    m = m < 0 ? 0 : (m > 255 ? 255 : m);
+                    p.db_u8[row + col] = (uint8_t) m;
+                }
+                acc[q] = 0.0f;
+            }
+            dcacc = 0.0f;
+        }
+    }
+}
+
+}  // namespace
+
+int launch_spectrum1024(const SpecParams& p, cudaStream_t stream)
+{
+    const uint64_t total = (uint64_t) p.n_streams * (uint64_t) p.n_rows;
+    if (total == 0) return B200_OK;
+    if (total >= (1ull << 31)) {
+        set_error("spectrum: n_streams * n_rows = %llu exceeds 2^31 - 1 rows per launch", (unsigned long long) total);
+        return B200_ERR_ARG;
+    }
+    const bool multi = p.K > 1;
+    const bool window = p.window != nullptr;
+    auto kern = multi ? (window ? spectrum1024_kernel<true, true> : spectrum1024_kernel<true, false>)
+                      : (window ? spectrum1024_kernel<false, true> : spectrum1024_kernel<false, false>);
+    static bool configured[4] = {false, false, false, false};
+    const int which = (multi ? 2 : 0) + (window ? 1 : 0);
+    if (!configured[which]) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM));
+        configured[which] = true;
+    }
+    int ctas_per_sm = 0;
+    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, WARPS_PER_CTA * 32, CTA_SMEM));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    // persistent grid: a whole number of CTAs per SM, never more warps than rows
+    uint64_t grid = (uint64_t) sm_count() * (uint64_t) ctas_per_sm;
+    const uint64_t needed = (total + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (grid > needed) grid = needed;
+    kern<<<(unsigned) grid, WARPS_PER_CTA * 32, CTA_SMEM, stream>>>(p);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,25 @@
+// spectrum_kernels.cuh -- parameter block shared by the spectrum kernels and their launcher.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+struct SpecParams {
+    const uint8_t* iq;            // stream 0, sample 0 (cmplx_u8 wire layout)
+    int64_t stream_stride_bytes;  // between streams
+    int n_streams;
+    int64_t n_rows;               // output rows per stream
+    int hop;                      // samples between the K frames of one row
+    int K;                        // frames accumulated per row
+    int64_t row_hop;              // samples between rows
+    float* db;                    // [n_streams][n_rows][N] or null
+    float* power;                 // [n_streams][n_rows][N] or null
+    uint8_t* db_u8;               // [n_streams][n_rows][N] or null
+    float db_offset;              // 10*log10(g / (K * 2^14)): folds gain, /count and the 1/128 input scale
+    const float2* twiddle;        // exp(-2*pi*i*k/N), k = 0..N-1 (device)
+    const float* window;          // N floats (device) or null = rectangular
+};
+
+}  // namespace b200

@@ -3,7 +3,7 @@
 All generators return ``uint8`` arrays of shape ``[n, 2]`` (re, im) in the RTL-SDR wire
 format the reference's ``cmplx_u8`` describes (common_sp.h:7-11): offset binary, 128 = 0.
 Pure numpy; shared by the tests, ``bench.py`` and ``tests/golden/make_golden.py`` so that
-the oracle and the GPU path always see the same bytes.
+the CPU checker and the GPU path always see the same bytes.
 """
 from __future__ import annotations
 

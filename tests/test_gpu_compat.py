@@ -1,0 +1,152 @@
+"""GPU parity of the reference-named interface (include/rtlws_compat.h) and of the
+host-buffer session: the calls an unmodified cbb_main.c / audio_main.c would make."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_spectrum_add_semantics(pkg, cuda, po, synth):
+    iq = synth.s2_tones(1024 * 6, seed=3)
+    s = pkg.spectrum_alloc(1024)
+    ps = np.zeros(1024)
+    for f in range(6):                                   # cbb_main.c:50-59
+        assert pkg.spectrum_add_cmplx_u8(s, iq[1024 * f:1024 * (f + 1)], ps, 1024) == 0
+    want = po.Spectrum(1024).rows(iq, K=6)[0]
+    np.testing.assert_allclose(ps, want, rtol=1e-4, atol=1e-4 * want.mean())
+    # accumulate into a dirty caller buffer, then the wrong length
+    rng = np.random.default_rng(4)
+    init = rng.uniform(0, 50, 1024)
+    a = init.copy()
+    assert pkg.spectrum_add_cmplx_u8(s, iq[:1024], a, 1024) == 0
+    b = init.copy()
+    po.Spectrum(1024).add_cmplx_u8(iq[:1024], b)
+    np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-4 * b.mean())
+    assert np.isclose(a[512], init[512] + a[511])
+    keep = a.copy()
+    assert pkg.spectrum_add_cmplx_u8(s, iq[:512], a, 512) == -1        # spectrum.c:51-52
+    assert np.array_equal(a, keep)
+    # the two caller-less input types
+    x32 = iq[:1024].astype(np.int32) - 128
+    c = np.zeros(1024)
+    assert pkg.spectrum_add_cmplx_s32(s, x32, c, 1024) == 0
+    d = np.zeros(1024)
+    po.Spectrum(1024).add_cmplx_s32(x32, d)
+    np.testing.assert_allclose(c, d, rtol=1e-4, atol=1e-4 * d.mean())
+    xr = rng.standard_normal(1024).astype(np.float32)
+    e = np.zeros(1024)
+    assert pkg.spectrum_add_real_f32(s, xr, e, 1024) == 0
+    f = np.zeros(1024)
+    po.Spectrum(1024).add_real_f32(xr, f)
+    np.testing.assert_allclose(e, f, rtol=1e-4, atol=1e-4 * f.mean())
+    pkg.spectrum_free(s)
+    s4 = pkg.spectrum_alloc(4096)
+    iq4 = synth.s2_tones(4096, N=4096)
+    g = np.zeros(4096)
+    assert pkg.spectrum_add_cmplx_u8(s4, iq4, g, 4096) == 0
+    np.testing.assert_allclose(g, po.Spectrum(4096).rows(iq4)[0], rtol=1e-4, atol=1e-4 * g.mean())
+    pkg.spectrum_free(s4)
+
+
+@pytest.mark.parametrize("R", [1, 5, 10, 16])
+def test_cic_decimate_bit_exact_with_state(pkg, cuda, po, synth, R):
+    iq = synth.s1_noise(R * 700, seed=R)
+    cut = R * 300
+    delay = pkg.CicDelayLine()
+    st = po.CicState()
+    for part in (iq[:cut], iq[cut:]):
+        dst = np.zeros((len(part) // R, 2), np.int32)
+        assert pkg.cic_decimate(R, part, len(part), dst, len(dst), delay) == 0
+        _, want, st = po.cic_decimate(R, part, st)
+        assert np.array_equal(dst, want)
+        assert [delay.integrator_prev_out.re, delay.integrator_prev_out.im] == list(st.integrator_prev_out)
+        assert [delay.comb_prev_in.re, delay.comb_prev_in.im] == list(st.comb_prev_in)
+    dst = np.zeros((10, 2), np.int32)
+    assert pkg.cic_decimate(R, iq[:R * 10], R * 10, dst, 9, delay) == -1      # resample.c:18-19
+    # a caller-set state with integrator != comb input only shifts the first output
+    odd = pkg.CicDelayLine()
+    odd.integrator_prev_out.re, odd.comb_prev_in.re = 1000, 400
+    ost = po.CicState()
+    ost.integrator_prev_out[0], ost.comb_prev_in[0] = 1000, 400
+    assert pkg.cic_decimate(R, iq[:R * 10], R * 10, dst, 10, odd) == 0
+    _, want, ost = po.cic_decimate(R, iq[:R * 10], ost)
+    assert np.array_equal(dst, want) and odd.integrator_prev_out.re == ost.integrator_prev_out[0]
+
+
+def test_halfband_decimate_with_delay_line(pkg, cuda, po):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(4096).astype(np.float32)
+    d_gpu = np.zeros(10, np.float32)
+    d_cpu = np.zeros(10, np.float32)
+    got, want = [], []
+    for lo, hi in ((0, 1000), (1000, 1020), (1020, 4096)):
+        out = np.zeros((hi - lo) // 2, np.float32)
+        pkg.halfband_decimate(x[lo:hi], out, len(out), d_gpu)
+        got.append(out)
+        want.append(po.halfband_decimate(x[lo:hi], d_cpu))
+        assert np.array_equal(d_gpu, d_cpu)
+    assert np.abs(np.concatenate(got) - np.concatenate(want)).max() <= 1e-6
+    imp = np.zeros(64, np.float32)
+    imp[0] = 1
+    out = np.zeros(32, np.float32)
+    pkg.halfband_decimate(imp, out, 32, np.zeros(10, np.float32))
+    np.testing.assert_allclose(out[:6], [0.01824, -0.11614, 0.34790, 0.34790, -0.11614, 0.01824], rtol=1e-6)
+
+
+def test_rf_decimator_reblocking_and_callbacks(pkg, cuda, po, synth):
+    iq = synth.s3_fm(2 * 204800 + 5000, seed=8)
+    d = pkg.RfDecimator()
+    seen = []
+    order = []
+    d.add_callback(lambda sig, n: (seen.append(sig.copy()), order.append("a")))
+    d.add_callback(lambda sig, n: order.append("b"))
+    assert d.decimate_cmplx_u8(iq[:100]) == -1                     # rf_decimator.c:90-91
+    assert d.set_parameters(0.0, 10) == -1 and d.set_parameters(2048000.0, 0) == -1
+    assert d.set_parameters(2048000.0, 10) == 0
+    for pos in range(0, len(iq), 131072):                          # source-buffer sized pushes
+        assert d.decimate_cmplx_u8(iq[pos:pos + 131072]) == 0
+    assert [len(s) for s in seen] == [20480, 20480] and order == ["a", "b", "a", "b"]
+    want, _ = po.chain_run(iq)
+    assert np.array_equal(np.concatenate(seen), want)
+    d.remove_callbacks()
+    assert d.decimate_cmplx_u8(iq[:204800]) == 0 and len(seen) == 2
+    # main.c:149-155: changing the rate re-derives the block sizes and forgets the surplus
+    assert d.set_parameters(1024000.0, 5) == 0
+    d.add_callback(lambda sig, n: seen.append(sig.copy()))
+    assert d.decimate_cmplx_u8(iq[:102400]) == 0
+    assert len(seen) == 3 and len(seen[2]) == 20480
+    d.free()
+
+
+def test_session_host_buffers(pkg, cuda, po, synth):
+    torch = cuda
+    n_streams, n = 6, 5120 * 6
+    iq = np.stack([synth.s3_fm(2 * n, seed=90 + s) for s in range(n_streams)])
+    sess = pkg.Session(n_streams, n)
+    h_iq = torch.empty((n_streams, n, 2), dtype=torch.uint8).pin_memory()
+    h_db = torch.empty((n_streams, n // 1024, 1024), dtype=torch.float32).pin_memory()
+    h_audio = torch.empty((n_streams, n // 40), dtype=torch.float32).pin_memory()
+    audio_parts = []
+    for b in range(2):                                             # two batches: history carries inside
+        h_iq.copy_(torch.as_tensor(iq[:, b * n:(b + 1) * n]))
+        sess.chain(h_iq, n, h_db, h_audio)
+        audio_parts.append(h_audio.numpy().copy())
+        for s in range(n_streams):
+            rows = po.Spectrum(1024).rows(iq[s, b * n:(b + 1) * n])
+            assert np.abs(h_db.numpy()[s] - 10 * np.log10(rows)).max() <= 0.01
+    got = np.concatenate(audio_parts, axis=1)
+    for s in range(n_streams):
+        _, dec, _ = po.cic_decimate(10, iq[s])
+        _, _, want, _ = po.fm_demodulate(dec)
+        assert np.abs(got[s] - want).max() <= 1e-4
+    # pageable host memory works too
+    sess.reset()
+    db2 = np.empty((n_streams, n // 1024, 1024), np.float32)
+    au2 = np.empty((n_streams, n // 40), np.float32)
+    sess.chain(np.ascontiguousarray(iq[:, :n]), n, db2, au2)
+    assert np.array_equal(au2, audio_parts[0])
+    with pytest.raises(pkg.B200Error):
+        sess.chain(h_iq, 5000, h_db, h_audio)
+    sess.close()
