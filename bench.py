@@ -46,7 +46,7 @@ UNIT = "Msamples/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=N_STREAMS)
@@ -107,12 +107,14 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (host time, csv line)
+        self.window = None
 
     def start(self):
+        """Start sampling (nvidia-smi needs ~100 ms to come up, so start before the warm-up)."""
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -121,12 +123,16 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self, t0: float, t1: float):
+        """Host-clock bounds of the timed region; only samples inside it are reported."""
+        self.window = (t0, t1)
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -134,7 +140,14 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        lines = self.lines
+        if self.window is not None:
+            inside = [(t, l) for t, l in lines if self.window[0] <= t <= self.window[1]]
+            if not inside and lines:      # region shorter than the sampling period: the closest sample
+                mid = 0.5 * (self.window[0] + self.window[1])
+                inside = [min(lines, key=lambda tl: abs(tl[0] - mid))]
+            lines = inside
+        for _, line in lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -165,9 +178,10 @@ def run_ref_bench(n_streams: int, samples_per_stream: int, workers: int, mode: s
     shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     path = os.path.join(shm, f"b200sdr_refbench_{os.getpid()}.bin")
     try:
+        unique = [pkg.synth.s3_fm(samples_per_stream, seed=1000 + s) for s in range(min(n_streams, 16))]
         with open(path, "wb") as f:
-            for s in range(n_streams):
-                pkg.synth.s3_fm(samples_per_stream, seed=1000 + s).tofile(f)
+            for s in range(n_streams):          # 16 distinct captures, repeated (timing is data-independent)
+                unique[s % len(unique)].tofile(f)
         res = subprocess.run([po.REF_BENCH, path, str(n_streams), str(samples_per_stream), str(workers), mode],
                              capture_output=True, text=True, timeout=900)
         if res.returncode != 0:
@@ -286,22 +300,25 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(False)
     sync_all()
 
     launches_before = pkg.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     t_start = torch.cuda.Event(enable_timing=True)
     t_stop = torch.cuda.Event(enable_timing=True)
     sync_all()
+    h0 = time.perf_counter()
     t_start.record(stream)
     for _ in range(args.steps):
         step(True)
     t_stop.record(stream)
     sync_all()
+    h1 = time.perf_counter()
+    sampler.mark(h0, h1)
     clocks = sampler.stop() if rank == 0 else None
     launches = pkg.launch_count() - launches_before
     elapsed_ms = t_start.elapsed_time(t_stop)
@@ -324,7 +341,7 @@ def main():
     alg_bytes = BYTES_PER_SAMPLE * n_local * L
     achieved = alg_bytes / (kern_ms_mean * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "b200_chain_exec (spectrum1024 + fm_chain on one pass)",
+                "traffic": None, "kernel": "chain_fused_kernel (b200_chain_exec: 1024-pt spectra + FM branch, one pass over the IQ)",
                 "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
     prof = os.path.join(ROOT, "profiles", "traffic.json")

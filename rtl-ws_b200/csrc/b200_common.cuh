@@ -115,6 +115,15 @@ __device__ __forceinline__ void tma_store_wait_read()
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
+// log2 on the MUFU unit, flush-to-zero form: no denormal pre-scaling instructions.  Inputs
+// here are sums of squares of integers (exact zero or >= 1), never denormal.  lg2(0) = -inf.
+__device__ __forceinline__ float lg2_ftz(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // streaming (evict-first) 32-bit store: spectra are written once and never re-read here
 __device__ __forceinline__ void st_stream_f32(float* p, float v)
 {

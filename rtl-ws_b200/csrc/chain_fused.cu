@@ -1,46 +1,184 @@
-// chain_fused.cu -- spectrum + FM branch on the same IQ bytes.
-// First cut: the two specialised kernels back to back on one stream (the IQ is read twice,
-// the second time largely from L2 for batches that fit).  The single-pass fused kernel
-// replaces the body of launch_chain_fused without touching its callers.
+// chain_fused.cu -- the full chain in ONE pass over the IQ bytes (sm_100a): per-frame
+// 1024-point dB spectra (K = 1, rectangular: spectrum.c + cbb_main.c:125) and the FM branch
+// at R = 10 (resample.c, common_sp.h:40-76, audio_main.c:110-139) from the same shared-memory
+// copy of the samples, so HBM sees each input byte once: 2 B in + 4 B dB + 0.1 B audio per
+// sample, the algorithmic minimum.
+//
+// Tile = 5120 samples = lcm(1024, 4 * 10): 5 frames and 128 audio samples, plus the FM
+// branch's 320-sample history (32 decimated samples) in front: 10880 bytes, fetched by one
+// TMA bulk copy into a two-deep ring.  A CTA is 5 warps:
+//   phase 1  all warps: CIC sums (dp4a) + atan2_approx + difference/limiter for the tile's
+//            544 decimated samples -> demod[] in shared memory;
+//            each warp unpacks ITS frame of the tile into registers;
+//   barrier  the input stage is free: re-arm the TMA for the tile two steps ahead;
+//   phase 2  half-band #1 -> work[] (266 values, shared);
+//   FFT      warp w: 32x32 two-pass transform of frame w, |X|^2, dB, coalesced stores;
+//   barrier
+//   phase 3  half-band #2 -> 128 audio floats, coalesced store.
+// Tiles are independent (a tile's audio depends on input bytes only, through the history),
+// so CTAs stride over (stream, tile) with no inter-CTA communication.
 #include "b200_common.cuh"
+#include "fft1024_warp.cuh"
 #include "fm_kernels.cuh"
-#include "spectrum_kernels.cuh"
 
 namespace b200 {
 
-int launch_spectrum1024(const SpecParams& p, cudaStream_t stream);
-int launch_fm_chain(const FmParams& p, cudaStream_t stream);
+namespace {
+
+constexpr int CF_WARPS = 5;
+constexpr int CF_THREADS = CF_WARPS * 32;
+constexpr int CF_TILE = 5120;                       // samples
+constexpr int CF_HIST = 320;                        // samples of history in front of a tile
+constexpr int CF_STAGE_BYTES = 2 * (CF_TILE + CF_HIST);   // 10880
+constexpr int CF_ND = (CF_TILE + CF_HIST) / 10;     // 544 decimated samples per tile
+constexpr int CF_NW = 2 * 128 + 10;                 // 266 first-stage outputs per tile
+constexpr int CF_SMEM = 2 * CF_STAGE_BYTES + CF_WARPS * FFT1024_XCH_BYTES + CF_ND * 4 + 272 * 4 + 16;
+
+struct ChainParams {
+    const uint8_t* iq;             // stream 0, first sample of the batch (history lies before it)
+    int64_t stream_stride_bytes;
+    int n_streams;
+    int tiles_per_stream;
+    float* db;                     // [n_streams][tiles_per_stream * 5][1024]
+    float* audio;                  // [n_streams][tiles_per_stream * 128], row stride audio_stride
+    int64_t audio_stride;
+    float dboff;                   // 10*log10(g) + FFT1024_DB_SHIFT
+    const float2* twiddle;
+};
+
+__global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    uint8_t* ring = smem;
+    float2* xch = reinterpret_cast<float2*>(smem + 2 * CF_STAGE_BYTES + warp * FFT1024_XCH_BYTES);
+    float* demod = reinterpret_cast<float*>(smem + 2 * CF_STAGE_BYTES + CF_WARPS * FFT1024_XCH_BYTES);
+    float* work = demod + CF_ND;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(work + 272);
+
+    const uint32_t tps = (uint32_t) p.tiles_per_stream;
+    const uint32_t total_tiles = (uint32_t) p.n_streams * tps;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](uint32_t tile, int st) {
+        const uint32_t s = tile / tps;
+        const uint32_t t = tile - s * tps;
+        const uint8_t* src = p.iq + (int64_t) s * p.stream_stride_bytes + 2 * ((int64_t) t * CF_TILE - CF_HIST);
+        mbar_arrive_expect_tx(&bars[st], CF_STAGE_BYTES);
+        tma_load_1d(ring + st * CF_STAGE_BYTES, src, CF_STAGE_BYTES, &bars[st]);
+    };
+
+    uint32_t tile = blockIdx.x;
+    if (tid == 0) {
+        if (tile < total_tiles) issue(tile, 0);
+        if (tile + gridDim.x < total_tiles) issue(tile + gridDim.x, 1);
+    }
+
+    float2 tw[32];
+    fft1024_load_twiddles(p.twiddle, lane, tw);
+
+    for (uint32_t it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        const uint32_t s = tile / tps;
+        const uint32_t t = tile - s * tps;
+        mbar_wait(&bars[st], (it >> 1) & 1);
+        const uint8_t* in = ring + st * CF_STAGE_BYTES;
+
+        // ---- phase 1: discriminator for the tile's 544 decimated samples (17 chunks of 32) ----
+        for (int c = warp; c < CF_ND / 32; c += CF_WARPS) {
+            const int j = 32 * c + lane;
+            uint32_t ure, uim;
+            cic10_sum(reinterpret_cast<const uint32_t*>(in + j * 20), ure, uim);
+            const float ph = atan2_approx_dev(__uint_as_float(uim) - CIC_MAGIC, __uint_as_float(ure) - CIC_MAGIC);
+            float prev = __shfl_up_sync(0xffffffffu, ph, 1);
+            if (lane == 0 && j > 0) {
+                cic10_sum(reinterpret_cast<const uint32_t*>(in + (j - 1) * 20), ure, uim);
+                prev = atan2_approx_dev(__uint_as_float(uim) - CIC_MAGIC, __uint_as_float(ure) - CIC_MAGIC);
+            }
+            demod[j] = fm_limit(ph, prev);          // demod[0] is never read
+        }
+        // ---- this warp's frame into registers ----
+        c64 a[32];
+        fft1024_load<false>(reinterpret_cast<const uint16_t*>(in + 2 * CF_HIST + 2048 * warp), nullptr, lane, a);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t nxt = tile + 2 * gridDim.x;
+            if (nxt < total_tiles) {
+                fence_proxy_async_smem();
+                issue(nxt, st);
+            }
+        }
+
+        // ---- phase 2: half-band #1 (audio_main.c:133); work index 0 <-> 2*n0 - 10 ----
+        for (int m = tid; m < CF_NW; m += CF_THREADS) {
+            const float* x = demod + 2 * m + 12;
+            work[m] = halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
+        }
+
+        // ---- spectrum of frame `warp` of this tile ----
+        float pw[32];
+        fft1024_core<true>(a, tw, xch, lane, pw);
+        // DC-position patch (spectrum.c:30-33): display index 512 takes display index 511's value
+        const float left = __shfl_sync(0xffffffffu, pw[31], 31);
+        if (lane == 0) pw[0] = left;
+        float* out = p.db + ((size_t) s * tps * 5 + (size_t) t * 5 + warp) * 1024 + lane;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) __stcs(out + fft1024_col(q), fmaf(DB_PER_LOG2, lg2_ftz(pw[q]), p.dboff));
+
+        __syncthreads();
+        // ---- phase 3: half-band #2 (audio_main.c:139) ----
+        if (tid < 128) {
+            const float* x = work + 2 * tid + 10;
+            p.audio[(int64_t) s * p.audio_stride + (int64_t) t * 128 + tid] =
+                halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
+        }
+    }
+}
+
+}  // namespace
 
 int launch_chain_fused(const uint8_t* d_iq, int64_t stride, int n_streams, int64_t n_samples, float db_offset,
                        const float2* twiddle, float* d_db, float* d_audio, int64_t audio_stride, cudaStream_t stream)
 {
-    SpecParams sp;
-    sp.iq = d_iq;
-    sp.stream_stride_bytes = stride;
-    sp.n_streams = n_streams;
-    sp.n_rows = n_samples / 1024;
-    sp.hop = 1024;
-    sp.K = 1;
-    sp.row_hop = 1024;
-    sp.db = d_db;
-    sp.power = nullptr;
-    sp.db_u8 = nullptr;
-    sp.db_offset = db_offset;
-    sp.twiddle = twiddle;
-    sp.window = nullptr;
-    int rc = launch_spectrum1024(sp, stream);
-    if (rc) return rc;
-    FmParams fp;
-    fp.iq = d_iq;
-    fp.stream_stride_bytes = stride;
-    fp.n_streams = n_streams;
-    fp.n_samples = n_samples;
-    fp.R = 10;
-    fp.audio = d_audio;
-    fp.audio_stride = audio_stride;
-    fp.decimated = nullptr;
-    fp.dec_stride = 0;
-    return launch_fm_chain(fp, stream);
+    const int64_t tiles_per_stream = n_samples / CF_TILE;
+    const int64_t total = (int64_t) n_streams * tiles_per_stream;
+    if (total == 0) return B200_OK;
+    if (total >= (1ll << 31) || tiles_per_stream * 5 * 1024 >= (1ll << 40)) {
+        set_error("chain: too many tiles in one launch (%lld)", (long long) total);
+        return B200_ERR_ARG;
+    }
+    ChainParams p;
+    p.iq = d_iq;
+    p.stream_stride_bytes = stride;
+    p.n_streams = n_streams;
+    p.tiles_per_stream = (int) tiles_per_stream;
+    p.db = d_db;
+    p.audio = d_audio;
+    p.audio_stride = audio_stride;
+    // the plan's offset is 10*log10(g / (K * 2^14)) with K = 1; the fused unpack carries 2^30
+    p.dboff = db_offset - 16.0f * DB_PER_LOG2;
+    p.twiddle = twiddle;
+    static bool configured = false;
+    if (!configured) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(chain_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM));
+        configured = true;
+    }
+    int ctas_per_sm = 0;
+    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, chain_fused_kernel, CF_THREADS, CF_SMEM));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    int64_t grid = (int64_t) sm_count() * ctas_per_sm;
+    if (grid > total) grid = total;
+    chain_fused_kernel<<<(unsigned) grid, CF_THREADS, CF_SMEM, stream>>>(p);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
 }
 
 }  // namespace b200

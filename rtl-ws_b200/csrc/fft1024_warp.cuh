@@ -1,0 +1,94 @@
+// fft1024_warp.cuh -- one warp transforms one 1024-point frame held in shared memory
+// (shared by spectrum1024.cu and chain_fused.cu).
+//
+// Decomposition 1024 = 32 x 32 with n = 32*n1 + n2, k = k1 + 32*k2:
+//   pass 1: lane n2 holds x[32*n1 + n2] (n1 = 0..31) in registers, 32-point FFT over n1,
+//           multiply by W_1024^(n2*k1) (lane-private twiddles kept in registers for the
+//           life of the persistent warp), write row k1 of a padded shared tile;
+//   pass 2: lane k1 reads its row (all n2), 32-point FFT over n2 -> bins k1 + 32*k2.
+// One shared-memory exchange per frame, warp-private (only __syncwarp).
+#pragma once
+
+#include "b200_common.cuh"
+#include "fft_regs.cuh"
+
+namespace b200 {
+
+constexpr int FFT1024_XCH_STRIDE = 34;                         // float2 per row: LDS.128 / STS.64 conflict-free
+constexpr int FFT1024_XCH_BYTES = 32 * FFT1024_XCH_STRIDE * 8;  // 8704 per warp
+constexpr float DB_PER_LOG2 = 3.01029995663981195f;            // 10 * log10(2)
+// The unpack leaves samples as (x - 128) * 256 (see fft1024_load); the reference wants
+// (x - 128) / 128 (spectrum.c:56-57): a factor 2^15 in amplitude, 2^30 in power -- exact.
+constexpr float FFT1024_POWER_SCALE = 1.0f / 1073741824.0f;
+constexpr float FFT1024_DB_SHIFT = -30.0f * DB_PER_LOG2;       // added to 10*log10(g/K)
+
+// lane-private inter-pass twiddles W_1024^(lane * k1), k1 = 1..31
+__device__ __forceinline__ void fft1024_load_twiddles(const float2* __restrict__ table, int lane, float2 (&tw)[32])
+{
+#pragma unroll
+    for (int k1 = 1; k1 < 32; ++k1) tw[k1] = __ldg(&table[(lane * k1) & 1023]);
+}
+
+// Unpack (spectrum.c:54-58).  A byte b OR-ed into mantissa bits 8..15 of 2^23 reads as the
+// float 2^23 + 256*b, exactly.  All values stay multiples of 256 below 2^29, so the +-
+// butterflies of pass 1 are exact on the BIASED values: differences are clean, sums carry the
+// bias along the all-sums path only, and just one output (k1 = 0) ends up holding
+// 32 * (2^23 + 256*128), which fft1024_core removes with a single subtraction instead of one
+// per sample.  With a window the bias has to go before the multiply.
+template <bool WINDOW>
+__device__ __forceinline__ void fft1024_load(const uint16_t* in16, const float* win, int lane, c64 (&a)[32])
+{
+    const c64 bias1 = cpack(8421376.0f, 8421376.0f);               // 2^23 + 256 * 128
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) {
+        const uint32_t v = in16[32 * n1 + lane];
+        a[n1] = cpack(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7504)),
+                      __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7514)));
+        if (WINDOW) {
+            const float w = win[32 * n1 + lane];
+            a[n1] = cmul2(csub(a[n1], bias1), cpack(w, w));
+        }
+    }
+}
+
+// Both passes.  On return pw[q] = |X[lane + 32 * bitrev<32>(q)]|^2 * 2^30 (raw power).
+// xch: this warp's exchange tile.  The caller must __syncwarp() between the last read of the
+// frame bytes and anything that overwrites them; xch reuse across frames is ordered by the
+// __syncwarp() inside the next call's exchange.
+template <bool BIASED>
+__device__ __forceinline__ void fft1024_core(c64 (&a)[32], const float2 (&tw)[32], float2* xch, int lane,
+                                             float (&pw)[32])
+{
+    fft_dif<32>(a);
+    if (BIASED) a[0] = csub(a[0], cpack(269484032.0f, 269484032.0f));   // 32 * (2^23 + 2^15)
+    __syncwarp();           // every lane is done reading xch for the previous frame
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        const int k1 = bitrev<32>(q);
+        const c64 v = (k1 == 0) ? a[q] : cmul(a[q], tw[k1].x, tw[k1].y);
+        reinterpret_cast<c64*>(xch)[k1 * FFT1024_XCH_STRIDE + lane] = v;
+    }
+    __syncwarp();
+    c64 b[32];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&xch[lane * FFT1024_XCH_STRIDE + 2 * m]);
+        b[2 * m] = v.x;
+        b[2 * m + 1] = v.y;
+    }
+    fft_dif<32>(b);
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        float re, im;
+        cunpack(b[q], re, im);
+        pw[q] = fmaf(re, re, im * im);
+    }
+}
+
+// display column (fftshift: spectrum.c:25) of register q for this lane, minus the lane itself
+__host__ __device__ constexpr int fft1024_col(int q)
+{
+    return 32 * ((bitrev<32>(q) + 16) & 31);
+}
+
+}  // namespace b200

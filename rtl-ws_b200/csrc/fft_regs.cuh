@@ -1,8 +1,16 @@
-// fft_regs.cuh -- fully unrolled in-register forward FFTs (radix-2 DIF, sizes 2..32).
+// fft_regs.cuh -- fully unrolled in-register forward FFTs (radix-2 DIF, sizes 2..32) on
+// PACKED complex numbers: one 64-bit register pair holds (re, im) and every butterfly is a
+// Blackwell f32x2 instruction (FADD2 / FMUL2 / FFMA2, sm_100 PTX add/mul/fma.rn.f32x2).
 //
-// One thread owns R complex points in registers.  All twiddles inside a size-R transform
-// are compile-time constants (multiples of 2*pi/32), so after unrolling every butterfly
-// is FADD/FMUL/FFMA with immediate operands.  Output is left in bit-reversed register
+// Why packed: the FP32 pipe retires 128 lanes/clk/SM either way (tools/ubench.cu measures
+// 125 scalar vs 128 packed results/clk/SM on B200), but a packed instruction carries two
+// results per ISSUE slot, and the spectrum kernel is issue-bound (profiles/).  The lane
+// swap and per-lane negation that complex arithmetic needs (multiply by -i, the cross terms
+// of a complex product) are operand modifiers in SASS (R.F32x2.LO_HI, .NP), so they cost
+// nothing: ptxas folds the mov.b64 shuffles below into the consuming instruction.
+//
+// One thread owns R complex points.  All twiddles inside a size-R transform are
+// compile-time constants (multiples of 2*pi/32).  Output is left in bit-reversed register
 // order; callers permute by renaming registers (bitrev<R>() is constexpr), which is free.
 //
 // Sign convention: X[k] = sum_j x[j] exp(-2*pi*i*j*k/R)  -- the FFTW_FORWARD transform the
@@ -10,8 +18,71 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace b200 {
+
+typedef unsigned long long c64;      // packed complex: low word = re, high word = im
+
+__device__ __forceinline__ c64 cpack(float re, float im)
+{
+    c64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(re), "f"(im));
+    return r;
+}
+__device__ __forceinline__ void cunpack(c64 v, float& re, float& im)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(re), "=f"(im) : "l"(v));
+}
+__device__ __forceinline__ c64 cadd(c64 a, c64 b)
+{
+    c64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ c64 csub(c64 a, c64 b)
+{
+    c64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ c64 cmul2(c64 a, c64 b)      // lane-wise product
+{
+    c64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ c64 cfma2(c64 a, c64 b, c64 c)   // lane-wise a * b + c
+{
+    c64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ c64 cswap(c64 a)              // (im, re): an operand modifier in SASS
+{
+    float re, im;
+    cunpack(a, re, im);
+    return cpack(im, re);
+}
+
+// t * (c - i*s) = (tr*c + ti*s, ti*c - tr*s) = t * (c, c) + (ti, -tr) * (s, s).
+// Both scalars are broadcast operands (immediate or R.F32 in SASS) and (ti, -tr) is the
+// .LO_HI.NP operand modifier: two instructions, no shuffles.
+__device__ __forceinline__ c64 cmul_cs(c64 t, float c, float s)
+{
+    float tr, ti;
+    cunpack(t, tr, ti);
+    return cfma2(t, cpack(c, c), cmul2(cpack(ti, -tr), cpack(s, s)));
+}
+
+// general complex product a * w with w = (wr, wi):  (ar*wr - ai*wi, ai*wr + ar*wi)
+//   = a * (wr, wr) + (-ai, ar) * (wi, wi)
+__device__ __forceinline__ c64 cmul(c64 a, float wr, float wi)
+{
+    float ar, ai;
+    cunpack(a, ar, ai);
+    return cfma2(a, cpack(wr, wr), cmul2(cpack(-ai, ar), cpack(wi, wi)));
+}
 
 // cos(2*pi*q/32), q = 0..8 (first octant + quadrant end)
 __host__ __device__ constexpr float cos32_table(int q)
@@ -51,27 +122,20 @@ __host__ __device__ constexpr int bitrev(int i)
 }
 
 // t * exp(-2*pi*i*q/32), 0 <= q < 16; q is a compile-time constant after unrolling
-__device__ __forceinline__ float2 mul_w32(float2 t, int q)
+__device__ __forceinline__ c64 mul_w32(c64 t, int q)
 {
-    const float h = 0.70710678118654752440f;
     if (q == 0) return t;
-    if (q == 8) return make_float2(t.y, -t.x);
-    if (q == 4) return make_float2((t.x + t.y) * h, (t.y - t.x) * h);
-    if (q == 12) return make_float2((t.y - t.x) * h, -(t.x + t.y) * h);
-    const float c = cos32(q);
-    const float s = sin32(q);
-    return make_float2(fmaf(t.y, s, t.x * c), fmaf(-t.x, s, t.y * c));
-}
-
-// general complex multiply a * w
-__device__ __forceinline__ float2 cmul(float2 a, float2 w)
-{
-    return make_float2(fmaf(-a.y, w.y, a.x * w.x), fmaf(a.x, w.y, a.y * w.x));
+    if (q == 8) {                            // * (-i): (ti, -tr)
+        float re, im;
+        cunpack(t, re, im);
+        return cpack(im, -re);
+    }
+    return cmul_cs(t, cos32(q), sin32(q));
 }
 
 // In-place forward DIF FFT of R points held in registers; result index bitrev<R>(p) is in a[p].
 template <int R>
-__device__ __forceinline__ void fft_dif(float2 (&a)[R])
+__device__ __forceinline__ void fft_dif(c64 (&a)[R])
 {
     static_assert(R == 2 || R == 4 || R == 8 || R == 16 || R == 32, "register FFT sizes");
 #pragma unroll
@@ -82,10 +146,10 @@ __device__ __forceinline__ void fft_dif(float2 (&a)[R])
             for (int k = 0; k < half; ++k) {
                 const int i = g + k;
                 const int j = i + half;
-                const float2 u = a[i];
-                const float2 v = a[j];
-                a[i] = make_float2(u.x + v.x, u.y + v.y);
-                a[j] = mul_w32(make_float2(u.x - v.x, u.y - v.y), k * (16 / half));
+                const c64 u = a[i];
+                const c64 v = a[j];
+                a[i] = cadd(u, v);
+                a[j] = mul_w32(csub(u, v), k * (16 / half));
             }
         }
     }

@@ -11,8 +11,9 @@
 //
 // A CTA walks tiles of T audio samples.  The tile's bytes ((4T + 32) * 2R, 10880 at
 // R = 10) are staged by the TMA unit into a two-deep shared ring; phases:
-//   1. one thread per decimated sample: byte sums with dp4a, atan2_approx -> phase[] (smem)
-//   2. one thread per first-stage output: diff, limiter, half-band -> work[] (smem)
+//   1. one thread per decimated sample: byte sums with dp4a, atan2_approx, first difference
+//      against the neighbour lane's phase (warp shuffle), limiter -> demod[] (smem)
+//   2. one thread per first-stage output: half-band -> work[] (smem)
 //   3. one thread per audio sample: half-band -> global
 #include "b200_common.cuh"
 #include "fm_kernels.cuh"
@@ -30,6 +31,23 @@ __host__ __device__ inline int fm_tile_audio(int R)
     return T;
 }
 
+// One warp-wide step of the discriminator: lane handles local decimated index j (bytes at
+// in + j * 2R); returns the phase (0 for j outside [0, nd)), and writes the CIC sums.
+template <int RT>
+__device__ __forceinline__ float fm_phase_at(const uint8_t* in, int R, int j, int nd, int& sre, int& sim)
+{
+    uint32_t ure = CIC_MAGIC_BITS, uim = CIC_MAGIC_BITS;
+    if (j >= 0 && j < nd) {
+        if (RT == 10)
+            cic10_sum(reinterpret_cast<const uint32_t*>(in + j * 20), ure, uim);
+        else
+            cic_sum(reinterpret_cast<const uint16_t*>(in) + (size_t) j * R, R, ure, uim);
+    }
+    sre = (int) (ure - CIC_MAGIC_BITS);
+    sim = (int) (uim - CIC_MAGIC_BITS);
+    return atan2_approx_dev(__uint_as_float(uim) - CIC_MAGIC, __uint_as_float(ure) - CIC_MAGIC);
+}
+
 // RT = 10: the default decimation (cbb_main.c:80), word loads + dp4a, fully unrolled.
 // RT = 0:  any R, sample-wise.
 template <int RT>
@@ -39,9 +57,10 @@ __global__ void __launch_bounds__(FM_THREADS) fm_chain_kernel(const FmParams p, 
     extern __shared__ __align__(128) uint8_t smem[];
     const int R = RT ? RT : p.R;
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
     uint8_t* ring = smem;
-    float* phase = reinterpret_cast<float*>(smem + 2 * stage_bytes);
-    float* work = phase + (4 * T + 32);
+    float* demod = reinterpret_cast<float*>(smem + 2 * stage_bytes);      // d[j], local index as below
+    float* work = demod + (4 * T + 32);
     uint64_t* bars = reinterpret_cast<uint64_t*>(work + (2 * T + 16));
 
     const int64_t n_audio = p.n_samples / (4 * R);
@@ -80,35 +99,24 @@ __global__ void __launch_bounds__(FM_THREADS) fm_chain_kernel(const FmParams p, 
         mbar_wait(&bars[st], (it >> 1) & 1);
         const uint8_t* in = ring + st * stage_bytes;
 
-        // ---- phase 1: CIC boxcar (resample.c:21-40) + atan2_approx ----
-        for (int j = tid; j < nd; j += FM_THREADS) {
+        // ---- phase 1: CIC boxcar (resample.c:21-40), atan2_approx, first difference and
+        //      limiter (audio_main.c:110-131).  Lanes hold consecutive j, so phase[j-1] comes
+        //      from the neighbour lane; lane 0 recomputes it. ----
+        for (int j0 = (tid & ~31); j0 < nd; j0 += FM_THREADS) {
+            const int j = j0 + lane;
             int sre, sim;
-            if (RT == 10) {
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(in + j * 20);
-                uint32_t ure = 0, uim = 0;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const uint32_t v = w[k];
-                    ure = __dp4a(v, 0x00010001u, ure);
-                    uim = __dp4a(v, 0x01000100u, uim);
-                }
-                sre = (int) ure - 1280;
-                sim = (int) uim - 1280;
-            } else {
-                const uint16_t* h = reinterpret_cast<const uint16_t*>(in) + (size_t) j * R;
-                uint32_t ure = 0, uim = 0;
-                for (int k = 0; k < R; ++k) {
-                    const uint32_t v = h[k];
-                    ure += v & 0xffu;
-                    uim += v >> 8;
-                }
-                sre = (int) ure - 128 * R;
-                sim = (int) uim - 128 * R;
+            const float ph = fm_phase_at<RT>(in, R, j, nd, sre, sim);
+            float prev = __shfl_up_sync(0xffffffffu, ph, 1);
+            if (lane == 0) {
+                int a, b;
+                prev = fm_phase_at<RT>(in, R, j - 1, nd, a, b);
             }
-            phase[j] = atan2_approx_dev(sim, sre);
-            if (p.decimated != nullptr && j >= 32) {
-                int2* dst = reinterpret_cast<int2*>(p.decimated) + (int64_t) s * p.dec_stride + (4 * n0 + (j - 32));
-                *dst = make_int2(sre, sim);
+            if (j < nd) {
+                demod[j] = fm_limit(ph, prev);
+                if (p.decimated != nullptr && j >= 32) {
+                    int2* dst = reinterpret_cast<int2*>(p.decimated) + (int64_t) s * p.dec_stride + (4 * n0 + (j - 32));
+                    *dst = make_int2(sre, sim);
+                }
             }
         }
         __syncthreads();
@@ -121,36 +129,23 @@ __global__ void __launch_bounds__(FM_THREADS) fm_chain_kernel(const FmParams p, 
             }
         }
 
-        // ---- phase 2: discriminator + limiter (audio_main.c:110-131), half-band #1 ----
-        const int nw = 2 * ta + 10;        // work index 0 <-> 2*n0 - 10
+        // ---- phase 2: half-band #1 (audio_main.c:133); work index 0 <-> 2*n0 - 10 ----
+        const int nw = 2 * ta + 10;
         for (int m = tid; m < nw; m += FM_THREADS) {
-            const int j = 2 * m + 12;      // demod index feeding tap k = 0
-            float ph[12];
-#pragma unroll
-            for (int k = 0; k < 12; ++k) ph[k] = phase[j - k];
-            // d(k) = limit(phase[j-k] - phase[j-k-1])
-            const float d0 = fm_limit(ph[0], ph[1]);
-            const float d2 = fm_limit(ph[2], ph[3]);
-            const float d4 = fm_limit(ph[4], ph[5]);
-            const float d5 = fm_limit(ph[5], ph[6]);
-            const float d6 = fm_limit(ph[6], ph[7]);
-            const float d8 = fm_limit(ph[8], ph[9]);
-            const float d10 = fm_limit(ph[10], ph[11]);
-            work[m] = halfband_taps(d0, d2, d4, d5, d6, d8, d10);
+            const float* x = demod + 2 * m + 12;        // x[-k] = demod sample feeding tap k
+            work[m] = halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
         }
         __syncthreads();
 
         // ---- phase 3: half-band #2 (audio_main.c:139) ----
         for (int a = tid; a < ta; a += FM_THREADS) {
-            const int m = 2 * a + 10;
-            const float v = halfband_taps(work[m], work[m - 2], work[m - 4], work[m - 5], work[m - 6], work[m - 8],
-                                          work[m - 10]);
-            p.audio[(int64_t) s * p.audio_stride + n0 + a] = v;
+            const float* x = work + 2 * a + 10;
+            p.audio[(int64_t) s * p.audio_stride + n0 + a] =
+                halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
         }
-        // phase[] / work[] are rewritten only after the next tile's barriers; the next
-        // iteration's phase-1 writes to phase[] cannot overtake phase-2 reads because of the
-        // __syncthreads above, and its phase-2 writes to work[] come after its own first
-        // __syncthreads, which every phase-3 reader of this tile has to reach first.
+        // demod[] is rewritten by the next tile's phase 1 only after every thread has passed the
+        // second __syncthreads above (all phase-2 reads done); work[] is rewritten in the next
+        // tile's phase 2, after its first __syncthreads, which every phase-3 reader reaches first.
     }
 }
 

@@ -13,27 +13,60 @@ namespace b200 {
 #define B200_HB4 0.34790f
 #define B200_HB5 0.5f
 
-// common_sp.h:40-76 on the CIC output (integers |v| <= 128*R).  The branch |y/x| < 1 is taken
-// on the integers (|y| < |x|), which is what the correctly rounded float quotient decides for
-// these magnitudes, so the quotient itself may carry a couple of ulps without ever flipping
-// the (discontinuous, 0.0083 rad) branch.
-__device__ __forceinline__ float atan2_approx_dev(int yi, int xi)
+// ---- CIC boxcar (resample.c:21-40) -----------------------------------------------------------
+// Sum of R u8 samples minus 128*R per component, exact.  The accumulator starts at the bit
+// pattern of the float 1.5 * 2^23 minus 128*R, so after the integer adds it IS the float
+// 1.5 * 2^23 + s: one FADD turns it into float(s) without an int->float conversion.
+constexpr uint32_t CIC_MAGIC_BITS = 0x4B400000u;       // 12582912.0f
+constexpr float CIC_MAGIC = 12582912.0f;
+
+// R = 10: five aligned 32-bit words = ten samples; dp4a sums bytes 0,2 (re) and 1,3 (im)
+__device__ __forceinline__ void cic10_sum(const uint32_t* w, uint32_t& ure, uint32_t& uim)
+{
+    ure = CIC_MAGIC_BITS - 1280u;
+    uim = CIC_MAGIC_BITS - 1280u;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const uint32_t v = w[k];
+        ure = __dp4a(v, 0x00010001u, ure);
+        uim = __dp4a(v, 0x01000100u, uim);
+    }
+}
+
+// any R, sample-wise
+__device__ __forceinline__ void cic_sum(const uint16_t* h, int R, uint32_t& ure, uint32_t& uim)
+{
+    ure = CIC_MAGIC_BITS - 128u * (uint32_t) R;
+    uim = CIC_MAGIC_BITS - 128u * (uint32_t) R;
+    for (int k = 0; k < R; ++k) {
+        const uint32_t v = h[k];
+        ure += v & 0xffu;
+        uim += v >> 8;
+    }
+}
+
+// ---- atan2_approx (common_sp.h:40-76) on the CIC output -----------------------------------------
+// x, y hold integers (|v| <= 128*R).  The reference computes z = y/x and then
+//   |z| < 1 : z / (1 + 0.28 z^2)            = x*y / (x^2 + 0.28 y^2)
+//   else    : pi/2 - z / (z^2 + 0.28)       = pi/2 - x*y / (y^2 + 0.28 x^2)
+// i.e. one quotient num/den with den = big^2 + 0.28 * small^2; the right-hand forms are used
+// here (one reciprocal instead of two divisions; x*y, x^2, y^2 are exact for |v| < 4096).
+// The branch (discontinuous by 0.0083 rad at |y| == |x|) is decided on the exact magnitudes,
+// which is what the correctly rounded quotient decides for integers of this size, so the
+// approximate reciprocal (2 ulp) can never flip it.  Quadrant fix-ups as in common_sp.h:61-74;
+// x == 0 falls out of the second form (num = 0), x == y == 0 is forced to 0 (common_sp.h:52-53).
+// Deviation from the reference sequence: a few f32 ulps (measured in tests: < 1e-6 rad).
+__device__ __forceinline__ float atan2_approx_dev(float y, float x)
 {
     const float pi = 3.14159265358979323846f;
     const float pi_by_2 = 1.57079632679489661923f;
-    if (xi == 0) return yi > 0 ? pi_by_2 : (yi == 0 ? 0.0f : -pi_by_2);
-    const float y = (float) yi;
-    const float x = (float) xi;
-    const float z = __fdiv_rn(y, x);
-    const int ay = yi < 0 ? -yi : yi;
-    const int ax = xi < 0 ? -xi : xi;
-    if (ay < ax) {
-        const float a = __fdiv_rn(z, fmaf(0.28f * z, z, 1.0f));
-        if (xi < 0) return yi < 0 ? a - pi : a + pi;
-        return a;
-    }
-    const float a = pi_by_2 - __fdiv_rn(z, fmaf(z, z, 0.28f));
-    return yi < 0 ? a - pi : a;
+    const float x2 = x * x;
+    const float y2 = y * y;
+    const bool lt = fabsf(y) < fabsf(x);
+    const float den = fmaf(0.28f, lt ? y2 : x2, lt ? x2 : y2);
+    const float q = __fdividef(x * y, den);
+    float r = lt ? (q + (x < 0.0f ? copysignf(pi, y) : 0.0f)) : (copysignf(pi_by_2, y) - q);
+    return den == 0.0f ? 0.0f : r;
 }
 
 // audio_main.c:117-130: first difference (no unwrap) then the +-1 hard limiter

@@ -19,7 +19,7 @@
 // warp-private two-deep ring guarded by mbarriers, so the next frame streams in from HBM
 // while the current one is in the butterflies.
 #include "b200_common.cuh"
-#include "fft_regs.cuh"
+#include "fft1024_warp.cuh"
 #include "spectrum_kernels.cuh"
 
 namespace b200 {
@@ -28,10 +28,10 @@ namespace {
 
 constexpr int N1024 = 1024;
 constexpr int FRAME_BYTES = 2 * N1024;             // u8 re + u8 im
-constexpr int XCH_STRIDE = 34;                     // float2 per row; 34 keeps LDS.128 and STS.64 conflict-free
-constexpr int XCH_BYTES = 32 * XCH_STRIDE * 8;     // 8704
+constexpr int XCH_BYTES = FFT1024_XCH_BYTES;
 constexpr int WARP_SMEM = 2 * FRAME_BYTES + XCH_BYTES + 32;   // ring + exchange tile + 2 mbarriers (padded)
 constexpr int WARPS_PER_CTA = 4;
+constexpr float POWER_SCALE = FFT1024_POWER_SCALE;
 constexpr int CTA_SMEM = WARPS_PER_CTA * WARP_SMEM + N1024 * 4;   // + window copy
 
 __device__ __forceinline__ const uint8_t* frame_src(const SpecParams& p, uint32_t item, int j)
@@ -43,8 +43,36 @@ __device__ __forceinline__ const uint8_t* frame_src(const SpecParams& p, uint32_
     return p.iq + (int64_t) s * p.stream_stride_bytes + 2 * ((int64_t) r * p.row_hop + (int64_t) j * p.hop);
 }
 
+// pw[q] holds the raw power of bin lane + 32 * bitrev(q); write the requested outputs of one
+// row in display order (fftshift = +16 on the k2 digit).  `base` = row * 1024 + lane, so every
+// store is base + a compile-time offset and a warp store covers 128 contiguous bytes.
+__device__ __forceinline__ void store_row(const SpecParams& p, float dboff, size_t base, const float (&pw)[32])
+{
+    if (p.db != nullptr) {
+        float* out = p.db + base;
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+            __stcs(out + fft1024_col(q), fmaf(DB_PER_LOG2, lg2_ftz(pw[q]), dboff));
+    }
+    if (p.power != nullptr) {
+        float* out = p.power + base;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) __stcs(out + fft1024_col(q), pw[q] * POWER_SCALE);
+    }
+    if (p.db_u8 != nullptr) {
+        uint8_t* out = p.db_u8 + base;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            // cbb_main.c:125-127: (int) truncation toward zero, then clamp; -inf / NaN -> 0
+            int m = __float2int_rz(fmaf(DB_PER_LOG2, lg2_ftz(pw[q]), dboff));
+            m = m < 0 ? 0 : (m > 255 ? 255 : m);
+            out[fft1024_col(q)] = (uint8_t) m;
+        }
+    }
+}
+
 template <bool MULTI, bool WINDOW>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) spectrum1024_kernel(const SpecParams p)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MULTI ? 2 : 3) spectrum1024_kernel(const SpecParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31;
@@ -74,10 +102,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) spectrum1024_kernel(con
     }
     __syncwarp();
 
-    // lane-private inter-pass twiddles W_1024^(lane * k1)
     float2 tw[32];
-#pragma unroll
-    for (int k1 = 1; k1 < 32; ++k1) tw[k1] = __ldg(&p.twiddle[(lane * k1) & (N1024 - 1)]);
+    fft1024_load_twiddles(p.twiddle, lane, tw);
+    // the plan's offset folds gain, /K and 2^-14; the unpack's extra 256^2 goes here
+    const float dboff = p.db_offset - 16.0f * DB_PER_LOG2;
 
     // producer cursor (lane 0 only cares)
     uint32_t ld_item = gw;
@@ -109,20 +137,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) spectrum1024_kernel(con
             const int st = f & 1;
             mbar_wait(&bars[st], (f >> 1) & 1);
 
-            // ---- unpack: byte -> float via the 2^23 magic constant (exact), minus 128 ----
-            float2 a[32];
-            const uint16_t* in16 = reinterpret_cast<const uint16_t*>(ring + st * FRAME_BYTES);
-#pragma unroll
-            for (int n1 = 0; n1 < 32; ++n1) {
-                const uint32_t v = in16[32 * n1 + lane];
-                a[n1].x = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540)) - 8388736.0f;
-                a[n1].y = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7541)) - 8388736.0f;
-                if (WINDOW) {
-                    const float w = win[32 * n1 + lane];
-                    a[n1].x *= w;
-                    a[n1].y *= w;
-                }
-            }
+            c64 a[32];
+            fft1024_load<WINDOW>(reinterpret_cast<const uint16_t*>(ring + st * FRAME_BYTES), win, lane, a);
             __syncwarp();
             // stage `st` is free again: request the frame two ahead
             if (lane == 0 && ld_left > 0) {
@@ -132,79 +148,29 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) spectrum1024_kernel(con
                 --ld_left;
                 if (++ld_j == K) { ld_j = 0; ld_item += GW; }
             }
-
-            // ---- pass 1: FFT over n1, twiddle, transpose through shared ----
-            fft_dif<32>(a);
-#pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                const int k1 = bitrev<32>(q);
-                const float2 v = (k1 == 0) ? a[q] : cmul(a[q], tw[k1]);
-                xch[k1 * XCH_STRIDE + lane] = v;
-            }
-            __syncwarp();
-            float2 b[32];
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const float4 v = *reinterpret_cast<const float4*>(&xch[lane * XCH_STRIDE + 2 * m]);
-                b[2 * m] = make_float2(v.x, v.y);
-                b[2 * m + 1] = make_float2(v.z, v.w);
-            }
-            // (the next frame's __syncwarp after its unpack orders these reads before its writes)
-
-            // ---- pass 2: FFT over n2 -> bins lane + 32 * bitrev(q) ----
-            fft_dif<32>(b);
+            float pw[32];
+            fft1024_core<!WINDOW>(a, tw, xch, lane, pw);
 
             if (!MULTI) {
-                float pw[32];
-#pragma unroll
-                for (int q = 0; q < 32; ++q) pw[q] = fmaf(b[q].x, b[q].x, b[q].y * b[q].y);
                 // DC-position patch (spectrum.c:30-33): display index N/2 (bin 0: lane 0, q 0)
                 // takes the value of display index N/2-1 (bin 1023: lane 31, q 31)
                 const float left = __shfl_sync(0xffffffffu, pw[31], 31);
                 if (lane == 0) pw[0] = left;
-                const size_t row = (size_t) item * N1024;
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const int k2 = bitrev<32>(q);
-                    const int col = lane + 32 * ((k2 + 16) & 31);     // fftshift
-                    const float db = fmaf(3.01029995663981195f, __log2f(pw[q]), p.db_offset);
-                    if (p.db) st_stream_f32(p.db + row + col, db);
-                    if (p.power) st_stream_f32(p.power + row + col, pw[q] * (1.0f / 16384.0f));
-                    if (p.db_u8) {
-                        int m = __float2int_rz(db);
-                        m = m < 0 ? 0 : (m > 255 ? 255 : m);
-                        p.db_u8[row + col] = (uint8_t) m;
-                    }
-                }
+                store_row(p, dboff, (size_t) item * N1024 + lane, pw);
             } else {
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const float pw = fmaf(b[q].x, b[q].x, b[q].y * b[q].y);
-                    acc[q] += pw;
-                    // cumulative DC patch: after K adds the DC position holds
-                    // sum_j (K - j) * |X_j[N-1]|^2, j = 0..K-1
-                    if (q == 31) dcacc = fmaf((float) (K - j), pw, dcacc);
-                }
+                for (int q = 0; q < 32; ++q) acc[q] += pw[q];
+                // cumulative DC patch: after K adds the DC position holds
+                // sum_j (K - j) * |X_j[N-1]|^2, j = 0..K-1
+                dcacc = fmaf((float) (K - j), pw[31], dcacc);
             }
         }
         if (MULTI) {
             const float left = __shfl_sync(0xffffffffu, dcacc, 31);
             if (lane == 0) acc[0] = left;
-            const size_t row = (size_t) item * N1024;
+            store_row(p, dboff, (size_t) item * N1024 + lane, acc);
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                const int k2 = bitrev<32>(q);
-                const int col = lane + 32 * ((k2 + 16) & 31);
-                const float db = fmaf(3.01029995663981195f, __log2f(acc[q]), p.db_offset);
-                if (p.db) st_stream_f32(p.db + row + col, db);
-                if (p.power) st_stream_f32(p.power + row + col, acc[q] * (1.0f / 16384.0f));
-                if (p.db_u8) {
-                    int m = __float2int_rz(db);
-                    m = m < 0 ? 0 : (m > 255 ? 255 : m);
-                    p.db_u8[row + col] = (uint8_t) m;
-                }
-                acc[q] = 0.0f;
-            }
+            for (int q = 0; q < 32; ++q) acc[q] = 0.0f;
             dcacc = 0.0f;
         }
     }

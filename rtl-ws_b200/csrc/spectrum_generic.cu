@@ -12,7 +12,6 @@
 // specialised kernel: unpack, forward DFT, fftshift, |X|^2 accumulate over K frames with the
 // cumulative DC-position patch, then the dB epilogue of cbb_main.c:125-128.
 #include "b200_common.cuh"
-#include "fft_regs.cuh"
 #include "spectrum_kernels.cuh"
 
 namespace b200 {
@@ -20,6 +19,11 @@ namespace b200 {
 namespace {
 
 enum InputKind { IN_CU8 = 0, IN_CS32 = 1, IN_RF32 = 2 };
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 w)
+{
+    return make_float2(fmaf(-a.y, w.y, a.x * w.x), fmaf(a.x, w.y, a.y * w.x));
+}
 
 constexpr int GEN_THREADS = 512;
 constexpr int GEN_SMEM_MAX_N = 8192;

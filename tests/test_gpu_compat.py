@@ -135,7 +135,8 @@ def test_session_host_buffers(pkg, cuda, po, synth):
         audio_parts.append(h_audio.numpy().copy())
         for s in range(n_streams):
             rows = po.Spectrum(1024).rows(iq[s, b * n:(b + 1) * n])
-            assert np.abs(h_db.numpy()[s] - 10 * np.log10(rows)).max() <= 0.01
+            ok = rows > 1e-6 * rows.mean(axis=1, keepdims=True)
+            assert np.abs(h_db.numpy()[s][ok] - 10 * np.log10(rows[ok])).max() <= 0.01
     got = np.concatenate(audio_parts, axis=1)
     for s in range(n_streams):
         _, dec, _ = po.cic_decimate(10, iq[s])
