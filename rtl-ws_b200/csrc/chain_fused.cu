@@ -6,15 +6,15 @@
 //
 // Tile = 5120 samples = lcm(1024, 4 * 10): 5 frames and 128 audio samples, plus the FM
 // branch's 320-sample history (32 decimated samples) in front: 10880 bytes, fetched by one
-// TMA bulk copy into a two-deep ring.  A CTA is 5 warps:
-//   phase 1  all warps: CIC sums (dp4a) + atan2_approx + difference/limiter for the tile's
-//            544 decimated samples -> demod[] in shared memory;
-//            each warp unpacks ITS frame of the tile into registers;
-//   barrier  the input stage is free: re-arm the TMA for the tile two steps ahead;
-//   phase 2  half-band #1 -> work[] (266 values, shared);
-//   FFT      warp w: 32x32 two-pass transform of frame w, |X|^2, dB, coalesced stores;
-//   barrier
-//   phase 3  half-band #2 -> 128 audio floats, coalesced store.
+// TMA bulk copy into a three-deep ring with full/empty mbarriers.  A CTA is 6 specialised
+// warps that never meet at a block barrier:
+//   warps 0-4  "spectrum": share the tile's discriminator work (CIC sums with dp4a,
+//              atan2_approx, difference + limiter for 544 decimated samples -> demod[], double
+//              buffered), then warp w unpacks frame w of the tile into registers, releases
+//              the stage, runs the 32x32 two-pass transform, |X|^2, dB, coalesced stores;
+//   warp 5     "audio": waits for demod[] of a tile (mbarrier), half-band #1 -> work[],
+//              half-band #2 -> 128 audio floats; it also drives the TMA producer side, which
+//              it can do promptly because it is idle most of the time.
 // Tiles are independent (a tile's audio depends on input bytes only, through the history),
 // so CTAs stride over (stream, tile) with no inter-CTA communication.
 #include "b200_common.cuh"
@@ -25,14 +25,17 @@ namespace b200 {
 
 namespace {
 
-constexpr int CF_WARPS = 5;
+constexpr int CF_FFT_WARPS = 5;
+constexpr int CF_WARPS = CF_FFT_WARPS + 1;
 constexpr int CF_THREADS = CF_WARPS * 32;
+constexpr int CF_STAGES = 3;
 constexpr int CF_TILE = 5120;                       // samples
 constexpr int CF_HIST = 320;                        // samples of history in front of a tile
 constexpr int CF_STAGE_BYTES = 2 * (CF_TILE + CF_HIST);   // 10880
 constexpr int CF_ND = (CF_TILE + CF_HIST) / 10;     // 544 decimated samples per tile
 constexpr int CF_NW = 2 * 128 + 10;                 // 266 first-stage outputs per tile
-constexpr int CF_SMEM = 2 * CF_STAGE_BYTES + CF_WARPS * FFT1024_XCH_BYTES + CF_ND * 4 + 272 * 4 + 16;
+constexpr int CF_SMEM = CF_STAGES * CF_STAGE_BYTES + CF_FFT_WARPS * FFT1024_XCH_BYTES + 2 * CF_ND * 4 + 272 * 4 +
+                        (2 * CF_STAGES + 4) * 8;
 
 struct ChainParams {
     const uint8_t* iq;             // stream 0, first sample of the batch (history lies before it)
@@ -53,92 +56,121 @@ __global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainP
     const int lane = tid & 31;
     const int warp = tid >> 5;
     uint8_t* ring = smem;
-    float2* xch = reinterpret_cast<float2*>(smem + 2 * CF_STAGE_BYTES + warp * FFT1024_XCH_BYTES);
-    float* demod = reinterpret_cast<float*>(smem + 2 * CF_STAGE_BYTES + CF_WARPS * FFT1024_XCH_BYTES);
-    float* work = demod + CF_ND;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(work + 272);
+    uint8_t* xch_base = smem + CF_STAGES * CF_STAGE_BYTES;
+    float* demod_base = reinterpret_cast<float*>(xch_base + CF_FFT_WARPS * FFT1024_XCH_BYTES);   // [2][CF_ND]
+    float* work = demod_base + 2 * CF_ND;
+    uint64_t* full = reinterpret_cast<uint64_t*>(work + 272);
+    uint64_t* empty = full + CF_STAGES;
+    uint64_t* demod_full = empty + CF_STAGES;       // [2]
+    uint64_t* demod_empty = demod_full + 2;         // [2]
 
     const uint32_t tps = (uint32_t) p.tiles_per_stream;
     const uint32_t total_tiles = (uint32_t) p.n_streams * tps;
+    const uint32_t first = blockIdx.x;
+    const uint32_t n_mine = first < total_tiles ? (total_tiles - first + gridDim.x - 1) / gridDim.x : 0;
 
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int i = 0; i < CF_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], CF_FFT_WARPS);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&demod_full[i], CF_FFT_WARPS);
+            mbar_init(&demod_empty[i], 1);
+        }
         fence_mbar_init();
     }
     __syncthreads();
 
-    auto issue = [&](uint32_t tile, int st) {
-        const uint32_t s = tile / tps;
-        const uint32_t t = tile - s * tps;
-        const uint8_t* src = p.iq + (int64_t) s * p.stream_stride_bytes + 2 * ((int64_t) t * CF_TILE - CF_HIST);
-        mbar_arrive_expect_tx(&bars[st], CF_STAGE_BYTES);
-        tma_load_1d(ring + st * CF_STAGE_BYTES, src, CF_STAGE_BYTES, &bars[st]);
-    };
+    if (warp == CF_FFT_WARPS) {
+        // =============================== audio warp (+ TMA producer) ===============================
+        auto issue = [&](uint32_t it) {
+            const uint32_t tile = first + it * gridDim.x;
+            const uint32_t s = tile / tps;
+            const uint32_t t = tile - s * tps;
+            const int st = it % CF_STAGES;
+            const uint8_t* src = p.iq + (int64_t) s * p.stream_stride_bytes + 2 * ((int64_t) t * CF_TILE - CF_HIST);
+            mbar_arrive_expect_tx(&full[st], CF_STAGE_BYTES);
+            tma_load_1d(ring + st * CF_STAGE_BYTES, src, CF_STAGE_BYTES, &full[st]);
+        };
+        if (lane == 0)
+            for (uint32_t it = 0; it < CF_STAGES - 1 && it < n_mine; ++it) issue(it);
 
-    uint32_t tile = blockIdx.x;
-    if (tid == 0) {
-        if (tile < total_tiles) issue(tile, 0);
-        if (tile + gridDim.x < total_tiles) issue(tile + gridDim.x, 1);
-    }
-
-    float2 tw[32];
-    fft1024_load_twiddles(p.twiddle, lane, tw);
-
-    for (uint32_t it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int st = it & 1;
-        const uint32_t s = tile / tps;
-        const uint32_t t = tile - s * tps;
-        mbar_wait(&bars[st], (it >> 1) & 1);
-        const uint8_t* in = ring + st * CF_STAGE_BYTES;
-
-        // ---- phase 1: discriminator for the tile's 544 decimated samples (17 chunks of 32) ----
-        for (int c = warp; c < CF_ND / 32; c += CF_WARPS) {
-            const int j = 32 * c + lane;
-            uint32_t ure, uim;
-            cic10_sum(reinterpret_cast<const uint32_t*>(in + j * 20), ure, uim);
-            const float ph = atan2_approx_dev(__uint_as_float(uim) - CIC_MAGIC, __uint_as_float(ure) - CIC_MAGIC);
-            float prev = __shfl_up_sync(0xffffffffu, ph, 1);
-            if (lane == 0 && j > 0) {
-                cic10_sum(reinterpret_cast<const uint32_t*>(in + (j - 1) * 20), ure, uim);
-                prev = atan2_approx_dev(__uint_as_float(uim) - CIC_MAGIC, __uint_as_float(ure) - CIC_MAGIC);
+        for (uint32_t it = 0; it < n_mine; ++it) {
+            // keep the ring full: tile it + STAGES - 1 goes into the stage tile it - 1 used
+            if (lane == 0 && it + CF_STAGES - 1 < n_mine) {
+                if (it > 0) mbar_wait(&empty[(it - 1) % CF_STAGES], ((it - 1) / CF_STAGES) & 1);
+                issue(it + CF_STAGES - 1);
             }
-            demod[j] = fm_limit(ph, prev);          // demod[0] is never read
-        }
-        // ---- this warp's frame into registers ----
-        c64 a[32];
-        fft1024_load<false>(reinterpret_cast<const uint16_t*>(in + 2 * CF_HIST + 2048 * warp), nullptr, lane, a);
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t nxt = tile + 2 * gridDim.x;
-            if (nxt < total_tiles) {
-                fence_proxy_async_smem();
-                issue(nxt, st);
+            __syncwarp();
+            const uint32_t tile = first + it * gridDim.x;
+            const uint32_t s = tile / tps;
+            const uint32_t t = tile - s * tps;
+            const int buf = it & 1;
+            const float* demod = demod_base + buf * CF_ND;
+            mbar_wait(&demod_full[buf], (it >> 1) & 1);
+
+            // ---- half-band #1 (audio_main.c:133); work index 0 <-> 2*n0 - 10 ----
+            for (int m = lane; m < CF_NW; m += 32) {
+                const float* x = demod + 2 * m + 12;
+                work[m] = halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
             }
-        }
-
-        // ---- phase 2: half-band #1 (audio_main.c:133); work index 0 <-> 2*n0 - 10 ----
-        for (int m = tid; m < CF_NW; m += CF_THREADS) {
-            const float* x = demod + 2 * m + 12;
-            work[m] = halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
-        }
-
-        // ---- spectrum of frame `warp` of this tile ----
-        float pw[32];
-        fft1024_core<true>(a, tw, xch, lane, pw);
-        // DC-position patch (spectrum.c:30-33): display index 512 takes display index 511's value
-        const float left = __shfl_sync(0xffffffffu, pw[31], 31);
-        if (lane == 0) pw[0] = left;
-        float* out = p.db + ((size_t) s * tps * 5 + (size_t) t * 5 + warp) * 1024 + lane;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&demod_empty[buf]);
+            // ---- half-band #2 (audio_main.c:139) ----
+            float* out = p.audio + (int64_t) s * p.audio_stride + (int64_t) t * 128;
 #pragma unroll
-        for (int q = 0; q < 32; ++q) __stcs(out + fft1024_col(q), fmaf(DB_PER_LOG2, lg2_ftz(pw[q]), p.dboff));
+            for (int r = 0; r < 4; ++r) {
+                const float* x = work + 2 * (32 * r + lane) + 10;
+                out[32 * r + lane] = halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
+            }
+            __syncwarp();       // work[] is rewritten by the next tile
+        }
+    } else {
+        // =============================== spectrum warps ===============================
+        float2* xch = reinterpret_cast<float2*>(xch_base + warp * FFT1024_XCH_BYTES);
+        float2 tw[32];
+        fft1024_load_twiddles(p.twiddle, lane, tw);
 
-        __syncthreads();
-        // ---- phase 3: half-band #2 (audio_main.c:139) ----
-        if (tid < 128) {
-            const float* x = work + 2 * tid + 10;
-            p.audio[(int64_t) s * p.audio_stride + (int64_t) t * 128 + tid] =
-                halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
+        for (uint32_t it = 0; it < n_mine; ++it) {
+            const int st = it % CF_STAGES;
+            const uint32_t tile = first + it * gridDim.x;
+            const uint32_t s = tile / tps;
+            const uint32_t t = tile - s * tps;
+            const int buf = it & 1;
+            float* demod = demod_base + buf * CF_ND;
+            mbar_wait(&full[st], (it / CF_STAGES) & 1);
+            const uint8_t* in = ring + st * CF_STAGE_BYTES;
+
+            // ---- discriminator share of this warp: chunks of 31 outputs (lane 0 only supplies
+            //      phase[j-1]); demod[buf] must have been drained by the audio warp (tile it - 2) ----
+            if (it >= 2) mbar_wait(&demod_empty[buf], ((it - 2) >> 1) & 1);
+            for (int c = warp; c < 18; c += CF_FFT_WARPS) {
+                const int j = 31 * c + lane;
+                uint32_t ure = CIC_MAGIC_BITS, uim = CIC_MAGIC_BITS;
+                if (j < CF_ND) cic10_sum(reinterpret_cast<const uint32_t*>(in + j * 20), ure, uim);
+                const float ph = atan2_approx_dev(__uint_as_float(uim) - CIC_MAGIC, __uint_as_float(ure) - CIC_MAGIC);
+                const float prev = __shfl_up_sync(0xffffffffu, ph, 1);
+                if (lane > 0 && j < CF_ND) demod[j] = fm_limit(ph, prev);     // demod[0] is never read
+            }
+
+            c64 a[32];
+            fft1024_load<false>(reinterpret_cast<const uint16_t*>(in + 2 * CF_HIST + 2048 * warp), nullptr, lane, a);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty[st]);
+                mbar_arrive(&demod_full[buf]);
+            }
+
+            float pw[32];
+            fft1024_core<true>(a, tw, xch, lane, pw);
+            // DC-position patch (spectrum.c:30-33): display index 512 takes display index 511's value
+            const float left = __shfl_sync(0xffffffffu, pw[31], 31);
+            if (lane == 0) pw[0] = left;
+            float* out = p.db + ((size_t) s * tps * 5 + (size_t) t * 5 + warp) * 1024 + lane;
+#pragma unroll
+            for (int k2 = 0; k2 < 32; ++k2)
+                __stcs(out + fft1024_col(k2), fmaf(DB_PER_LOG2, lg2_ftz(pw[k2]), p.dboff));
         }
     }
 }

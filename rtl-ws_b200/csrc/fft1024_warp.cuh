@@ -25,6 +25,7 @@ constexpr float FFT1024_DB_SHIFT = -30.0f * DB_PER_LOG2;       // added to 10*lo
 // lane-private inter-pass twiddles W_1024^(lane * k1), k1 = 1..31
 __device__ __forceinline__ void fft1024_load_twiddles(const float2* __restrict__ table, int lane, float2 (&tw)[32])
 {
+    tw[0] = make_float2(1.0f, 0.0f);
 #pragma unroll
     for (int k1 = 1; k1 < 32; ++k1) tw[k1] = __ldg(&table[(lane * k1) & 1023]);
 }
@@ -42,53 +43,53 @@ __device__ __forceinline__ void fft1024_load(const uint16_t* in16, const float* 
 #pragma unroll
     for (int n1 = 0; n1 < 32; ++n1) {
         const uint32_t v = in16[32 * n1 + lane];
-        a[n1] = cpack(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7504)),
-                      __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7514)));
+        const int r = bitrev<32>(n1);          // DIT wants its input in bit-reversed register order
+        a[r] = cpack(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7504)),
+                     __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7514)));
         if (WINDOW) {
             const float w = win[32 * n1 + lane];
-            a[n1] = cmul2(csub(a[n1], bias1), cpack(w, w));
+            a[r] = cmul2(csub(a[r], bias1), cpack(w, w));
         }
     }
 }
 
-// Both passes.  On return pw[q] = |X[lane + 32 * bitrev<32>(q)]|^2 * 2^30 (raw power).
-// xch: this warp's exchange tile.  The caller must __syncwarp() between the last read of the
-// frame bytes and anything that overwrites them; xch reuse across frames is ordered by the
-// __syncwarp() inside the next call's exchange.
+// Both passes.  `a` as left by fft1024_load.  On return pw[k2] = |X[lane + 32 * k2]|^2 * 2^30
+// (raw power).  xch: this warp's exchange tile.  The caller must __syncwarp() between the last
+// read of the frame bytes and anything that overwrites them; xch reuse across frames is
+// ordered by the __syncwarp() before the writes below.
+// The inter-pass twiddles W_1024^(n2*k1) are applied on the READ side (lane = k1, register
+// n2 -- the table is symmetric, so the same lane-private tw[] serves) fused into pass 2's first
+// butterfly stage.
 template <bool BIASED>
 __device__ __forceinline__ void fft1024_core(c64 (&a)[32], const float2 (&tw)[32], float2* xch, int lane,
                                              float (&pw)[32])
 {
-    fft_dif<32>(a);
+    fft_dit32<false>(a, tw);
     if (BIASED) a[0] = csub(a[0], cpack(269484032.0f, 269484032.0f));   // 32 * (2^23 + 2^15)
     __syncwarp();           // every lane is done reading xch for the previous frame
 #pragma unroll
-    for (int q = 0; q < 32; ++q) {
-        const int k1 = bitrev<32>(q);
-        const c64 v = (k1 == 0) ? a[q] : cmul(a[q], tw[k1].x, tw[k1].y);
-        reinterpret_cast<c64*>(xch)[k1 * FFT1024_XCH_STRIDE + lane] = v;
-    }
+    for (int k1 = 0; k1 < 32; ++k1) reinterpret_cast<c64*>(xch)[k1 * FFT1024_XCH_STRIDE + lane] = a[k1];
     __syncwarp();
     c64 b[32];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
         const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&xch[lane * FFT1024_XCH_STRIDE + 2 * m]);
-        b[2 * m] = v.x;
-        b[2 * m + 1] = v.y;
+        b[bitrev<32>(2 * m)] = v.x;
+        b[bitrev<32>(2 * m + 1)] = v.y;
     }
-    fft_dif<32>(b);
+    fft_dit32<true>(b, tw);
 #pragma unroll
-    for (int q = 0; q < 32; ++q) {
+    for (int k2 = 0; k2 < 32; ++k2) {
         float re, im;
-        cunpack(b[q], re, im);
-        pw[q] = fmaf(re, re, im * im);
+        cunpack(b[k2], re, im);
+        pw[k2] = fmaf(re, re, im * im);
     }
 }
 
-// display column (fftshift: spectrum.c:25) of register q for this lane, minus the lane itself
-__host__ __device__ constexpr int fft1024_col(int q)
+// display column (fftshift: spectrum.c:25) of pw[k2] for this lane, minus the lane itself
+__host__ __device__ constexpr int fft1024_col(int k2)
 {
-    return 32 * ((bitrev<32>(q) + 16) & 31);
+    return 32 * ((k2 + 16) & 31);
 }
 
 }  // namespace b200

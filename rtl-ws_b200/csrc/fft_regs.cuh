@@ -133,6 +133,76 @@ __device__ __forceinline__ c64 mul_w32(c64 t, int q)
     return cmul_cs(t, cos32(q), sin32(q));
 }
 
+// One DIT butterfly with twiddle W = exp(-2*pi*i*q/32) on v:  (u, v) -> (u + v*W, u - v*W).
+// General W: u + v*W is two chained FFMA2 (v*(c,c) + (vi,-vr)*(s,s) + u) and the other output
+// is 2u - (u + v*W), one more FFMA2: three packed instructions instead of four.
+__device__ __forceinline__ void dit_butterfly(c64& u, c64& v, int q)
+{
+    if (q == 0) {
+        const c64 s = cadd(u, v);
+        v = csub(u, v);
+        u = s;
+        return;
+    }
+    float vr, vi;
+    cunpack(v, vr, vi);
+    if (q == 8) {                            // v * (-i) = (vi, -vr)
+        const c64 t = cpack(vi, -vr);
+        const c64 s = cadd(u, t);
+        v = csub(u, t);
+        u = s;
+        return;
+    }
+    const float c = cos32(q);
+    const float sn = sin32(q);
+    const c64 s = cfma2(v, cpack(c, c), cfma2(cpack(vi, -vr), cpack(sn, sn), u));
+    float sr, si;
+    cunpack(s, sr, si);
+    v = cfma2(u, cpack(2.0f, 2.0f), cpack(-sr, -si));
+    u = s;
+}
+
+// First DIT stage with per-input complex pre-multipliers (the inter-pass twiddles):
+// (a, b) -> (ta*a + tb*b, ta*a - tb*b) in five packed instructions (three when ta == 1).
+__device__ __forceinline__ void dit_butterfly_pretwiddled(c64& a, c64& b, bool a_unit, float2 ta, float2 tb)
+{
+    c64 p = a;
+    if (!a_unit) p = cmul(a, ta.x, ta.y);
+    float br, bi;
+    cunpack(b, br, bi);
+    const c64 s = cfma2(b, cpack(tb.x, tb.x), cfma2(cpack(-bi, br), cpack(tb.y, tb.y), p));
+    float sr, si;
+    cunpack(s, sr, si);
+    b = cfma2(p, cpack(2.0f, 2.0f), cpack(-sr, -si));
+    a = s;
+}
+
+// In-place forward DIT FFT of 32 points.  Input: a[p] = x[bitrev<32>(p)] (bit-reversed order);
+// output in natural order a[k] = X[k].  If PRETW, input x[n] is first multiplied by tw[n]
+// (tw[0] is taken as 1), fused into the first stage.
+template <bool PRETW>
+__device__ __forceinline__ void fft_dit32(c64 (&a)[32], const float2 (&tw)[32])
+{
+#pragma unroll
+    for (int g = 0; g < 32; g += 2) {
+        if (PRETW) {
+            const int na = bitrev<32>(g);
+            const int nb = bitrev<32>(g + 1);
+            dit_butterfly_pretwiddled(a[g], a[g + 1], na == 0, tw[na], tw[nb]);
+        } else {
+            dit_butterfly(a[g], a[g + 1], 0);
+        }
+    }
+#pragma unroll
+    for (int half = 2; half <= 16; half <<= 1) {
+#pragma unroll
+        for (int g = 0; g < 32; g += 2 * half) {
+#pragma unroll
+            for (int k = 0; k < half; ++k) dit_butterfly(a[g + k], a[g + k + half], k * (16 / half));
+        }
+    }
+}
+
 // In-place forward DIF FFT of R points held in registers; result index bitrev<R>(p) is in a[p].
 template <int R>
 __device__ __forceinline__ void fft_dif(c64 (&a)[R])

@@ -34,14 +34,37 @@ constexpr int WARPS_PER_CTA = 4;
 constexpr float POWER_SCALE = FFT1024_POWER_SCALE;
 constexpr int CTA_SMEM = WARPS_PER_CTA * WARP_SMEM + N1024 * 4;   // + window copy
 
-__device__ __forceinline__ const uint8_t* frame_src(const SpecParams& p, uint32_t item, int j)
-{
-    // item = stream * n_rows + row; 32-bit division: total items < 2^31 is enforced by the launcher
-    const uint32_t n_rows = (uint32_t) p.n_rows;
-    const uint32_t s = item / n_rows;
-    const uint32_t r = item - s * n_rows;
-    return p.iq + (int64_t) s * p.stream_stride_bytes + 2 * ((int64_t) r * p.row_hop + (int64_t) j * p.hop);
-}
+// TMA producer cursor of one warp (only lane 0 uses it): walks the warp's rows, stride GW, and
+// the K frames of each row, without a division per frame.
+struct FrameCursor {
+    uint32_t s, r, left;
+    int j;
+    __device__ __forceinline__ void init(const SpecParams& p, uint32_t item, uint32_t frames)
+    {
+        const uint32_t n_rows = (uint32_t) p.n_rows;
+        s = item / n_rows;
+        r = item - s * n_rows;
+        j = 0;
+        left = frames;
+    }
+    __device__ __forceinline__ const uint8_t* src(const SpecParams& p) const
+    {
+        return p.iq + (int64_t) s * p.stream_stride_bytes + 2 * ((int64_t) r * p.row_hop + (int64_t) j * p.hop);
+    }
+    __device__ __forceinline__ void advance(const SpecParams& p, int K, uint32_t GW)
+    {
+        --left;
+        if (++j == K) {
+            j = 0;
+            r += GW;
+            const uint32_t n_rows = (uint32_t) p.n_rows;
+            while (r >= n_rows) {
+                r -= n_rows;
+                ++s;
+            }
+        }
+    }
+};
 
 // pw[q] holds the raw power of bin lane + 32 * bitrev(q); write the requested outputs of one
 // row in display order (fftshift = +16 on the k2 digit).  `base` = row * 1024 + lane, so every
@@ -107,18 +130,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MULTI ? 2 : 3) spectrum102
     // the plan's offset folds gain, /K and 2^-14; the unpack's extra 256^2 goes here
     const float dboff = p.db_offset - 16.0f * DB_PER_LOG2;
 
-    // producer cursor (lane 0 only cares)
-    uint32_t ld_item = gw;
-    int ld_j = 0;
-    uint32_t ld_left = n_items * (uint32_t) K;   // frames not yet requested
+    FrameCursor cur;
+    cur.init(p, gw, n_items * (uint32_t) K);
     if (lane == 0) {
 #pragma unroll
         for (int st = 0; st < 2; ++st) {
-            if (ld_left > 0) {
+            if (cur.left > 0) {
                 mbar_arrive_expect_tx(&bars[st], FRAME_BYTES);
-                tma_load_1d(ring + st * FRAME_BYTES, frame_src(p, ld_item, ld_j), FRAME_BYTES, &bars[st]);
-                --ld_left;
-                if (++ld_j == K) { ld_j = 0; ld_item += GW; }
+                tma_load_1d(ring + st * FRAME_BYTES, cur.src(p), FRAME_BYTES, &bars[st]);
+                cur.advance(p, K, GW);
             }
         }
     }
@@ -141,12 +161,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MULTI ? 2 : 3) spectrum102
             fft1024_load<WINDOW>(reinterpret_cast<const uint16_t*>(ring + st * FRAME_BYTES), win, lane, a);
             __syncwarp();
             // stage `st` is free again: request the frame two ahead
-            if (lane == 0 && ld_left > 0) {
+            if (lane == 0 && cur.left > 0) {
                 fence_proxy_async_smem();
                 mbar_arrive_expect_tx(&bars[st], FRAME_BYTES);
-                tma_load_1d(ring + st * FRAME_BYTES, frame_src(p, ld_item, ld_j), FRAME_BYTES, &bars[st]);
-                --ld_left;
-                if (++ld_j == K) { ld_j = 0; ld_item += GW; }
+                tma_load_1d(ring + st * FRAME_BYTES, cur.src(p), FRAME_BYTES, &bars[st]);
+                cur.advance(p, K, GW);
             }
             float pw[32];
             fft1024_core<!WINDOW>(a, tw, xch, lane, pw);
