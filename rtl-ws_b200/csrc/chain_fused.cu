@@ -6,17 +6,18 @@
 //
 // Tile = 5120 samples = lcm(1024, 4 * 10): 5 frames and 128 audio samples, plus the FM
 // branch's 320-sample history (32 decimated samples) in front: 10880 bytes, fetched by one
-// TMA bulk copy into a three-deep ring with full/empty mbarriers.  A CTA is 6 specialised
-// warps that never meet at a block barrier:
-//   warps 0-4  "spectrum": share the tile's discriminator work (CIC sums with dp4a,
-//              atan2_approx, difference + limiter for 544 decimated samples -> demod[], double
-//              buffered), then warp w unpacks frame w of the tile into registers, releases
-//              the stage, runs the 32x32 two-pass transform, |X|^2, dB, coalesced stores;
-//   warp 5     "audio": waits for demod[] of a tile (mbarrier), half-band #1 -> work[],
-//              half-band #2 -> 128 audio floats; it also drives the TMA producer side, which
-//              it can do promptly because it is idle most of the time.
-// Tiles are independent (a tile's audio depends on input bytes only, through the history),
-// so CTAs stride over (stream, tile) with no inter-CTA communication.
+// TMA bulk copy into a three-deep ring with full/empty mbarriers.  A CTA is 6 symmetric warps
+// that never meet at a block barrier.  For every tile each warp
+//   - does a third of a sixth... precisely 3 of the tile's 18 discriminator chunks (CIC sums
+//     with dp4a, atan2_approx, difference + limiter -> demod[], double buffered),
+//   - and 5 of the 6 warps unpack one frame each into registers, release the stage, run the
+//     32x32 two-pass transform, |X|^2, dB and store 4 KB of spectrum;
+//   - the sixth warp (rotating: tile index mod 6) is the tile's service warp: it re-arms the
+//     TMA producer and runs the two half-band decimators of the PREVIOUS tile -> 128 audio
+//     floats.  Its job is about a third of a transform, so it simply gets ahead.
+// All 12 warps an SM holds (two CTAs at <= 168 registers) are transform-capable; none idles
+// on a role.  Tiles are independent (a tile's audio depends on input bytes only, through the
+// history), so CTAs stride over (stream, tile) with no inter-CTA communication.
 #include "b200_common.cuh"
 #include "fft1024_warp.cuh"
 #include "fm_kernels.cuh"
@@ -25,8 +26,7 @@ namespace b200 {
 
 namespace {
 
-constexpr int CF_FFT_WARPS = 5;
-constexpr int CF_WARPS = CF_FFT_WARPS + 1;
+constexpr int CF_WARPS = 6;
 constexpr int CF_THREADS = CF_WARPS * 32;
 constexpr int CF_STAGES = 3;
 constexpr int CF_TILE = 5120;                       // samples
@@ -34,7 +34,8 @@ constexpr int CF_HIST = 320;                        // samples of history in fro
 constexpr int CF_STAGE_BYTES = 2 * (CF_TILE + CF_HIST);   // 10880
 constexpr int CF_ND = (CF_TILE + CF_HIST) / 10;     // 544 decimated samples per tile
 constexpr int CF_NW = 2 * 128 + 10;                 // 266 first-stage outputs per tile
-constexpr int CF_SMEM = CF_STAGES * CF_STAGE_BYTES + CF_FFT_WARPS * FFT1024_XCH_BYTES + 2 * CF_ND * 4 + 272 * 4 +
+constexpr int CF_WORK = 272;                        // CF_NW padded
+constexpr int CF_SMEM = CF_STAGES * CF_STAGE_BYTES + CF_WARPS * FFT1024_XCH_BYTES + 2 * CF_ND * 4 + 2 * CF_WORK * 4 +
                         (2 * CF_STAGES + 4) * 8;
 
 struct ChainParams {
@@ -57,9 +58,10 @@ __global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainP
     const int warp = tid >> 5;
     uint8_t* ring = smem;
     uint8_t* xch_base = smem + CF_STAGES * CF_STAGE_BYTES;
-    float* demod_base = reinterpret_cast<float*>(xch_base + CF_FFT_WARPS * FFT1024_XCH_BYTES);   // [2][CF_ND]
-    float* work = demod_base + 2 * CF_ND;
-    uint64_t* full = reinterpret_cast<uint64_t*>(work + 272);
+    float2* xch = reinterpret_cast<float2*>(xch_base + warp * FFT1024_XCH_BYTES);
+    float* demod_base = reinterpret_cast<float*>(xch_base + CF_WARPS * FFT1024_XCH_BYTES);   // [2][CF_ND]
+    float* work_base = demod_base + 2 * CF_ND;                                               // [2][CF_WORK]
+    uint64_t* full = reinterpret_cast<uint64_t*>(work_base + 2 * CF_WORK);
     uint64_t* empty = full + CF_STAGES;
     uint64_t* demod_full = empty + CF_STAGES;       // [2]
     uint64_t* demod_empty = demod_full + 2;         // [2]
@@ -69,110 +71,119 @@ __global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainP
     const uint32_t first = blockIdx.x;
     const uint32_t n_mine = first < total_tiles ? (total_tiles - first + gridDim.x - 1) / gridDim.x : 0;
 
+    auto issue = [&](uint32_t it) {
+        const uint32_t tile = first + it * gridDim.x;
+        const uint32_t s = tile / tps;
+        const uint32_t t = tile - s * tps;
+        const int st = it % CF_STAGES;
+        const uint8_t* src = p.iq + (int64_t) s * p.stream_stride_bytes + 2 * ((int64_t) t * CF_TILE - CF_HIST);
+        mbar_arrive_expect_tx(&full[st], CF_STAGE_BYTES);
+        tma_load_1d(ring + st * CF_STAGE_BYTES, src, CF_STAGE_BYTES, &full[st]);
+    };
+    // the two half-band decimators of local tile `it` (audio_main.c:133,139); one warp
+    auto audio_job = [&](uint32_t it) {
+        const uint32_t tile = first + it * gridDim.x;
+        const uint32_t s = tile / tps;
+        const uint32_t t = tile - s * tps;
+        const int buf = it & 1;
+        const float* demod = demod_base + buf * CF_ND;
+        float* work = work_base + buf * CF_WORK;
+        mbar_wait(&demod_full[buf], (it >> 1) & 1);
+        for (int m = lane; m < CF_NW; m += 32) {            // work index 0 <-> 2*n0 - 10
+            const float* x = demod + 2 * m + 12;
+            work[m] = halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&demod_empty[buf]);
+        float* out = p.audio + (int64_t) s * p.audio_stride + (int64_t) t * 128;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float* x = work + 2 * (32 * r + lane) + 10;
+            out[32 * r + lane] = halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
+        }
+    };
+
     if (tid == 0) {
         for (int i = 0; i < CF_STAGES; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], CF_FFT_WARPS);
+            mbar_init(&empty[i], CF_WARPS);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&demod_full[i], CF_FFT_WARPS);
+            mbar_init(&demod_full[i], CF_WARPS);
             mbar_init(&demod_empty[i], 1);
         }
         fence_mbar_init();
+        for (uint32_t it = 0; it < CF_STAGES - 1 && it < n_mine; ++it) issue(it);
     }
     __syncthreads();
 
-    if (warp == CF_FFT_WARPS) {
-        // =============================== audio warp (+ TMA producer) ===============================
-        auto issue = [&](uint32_t it) {
-            const uint32_t tile = first + it * gridDim.x;
-            const uint32_t s = tile / tps;
-            const uint32_t t = tile - s * tps;
-            const int st = it % CF_STAGES;
-            const uint8_t* src = p.iq + (int64_t) s * p.stream_stride_bytes + 2 * ((int64_t) t * CF_TILE - CF_HIST);
-            mbar_arrive_expect_tx(&full[st], CF_STAGE_BYTES);
-            tma_load_1d(ring + st * CF_STAGE_BYTES, src, CF_STAGE_BYTES, &full[st]);
-        };
-        if (lane == 0)
-            for (uint32_t it = 0; it < CF_STAGES - 1 && it < n_mine; ++it) issue(it);
+    float2 tw[32];
+    fft1024_load_twiddles(p.twiddle, lane, tw);
 
-        for (uint32_t it = 0; it < n_mine; ++it) {
-            // keep the ring full: tile it + STAGES - 1 goes into the stage tile it - 1 used
-            if (lane == 0 && it + CF_STAGES - 1 < n_mine) {
-                if (it > 0) mbar_wait(&empty[(it - 1) % CF_STAGES], ((it - 1) / CF_STAGES) & 1);
-                issue(it + CF_STAGES - 1);
-            }
-            __syncwarp();
-            const uint32_t tile = first + it * gridDim.x;
-            const uint32_t s = tile / tps;
-            const uint32_t t = tile - s * tps;
-            const int buf = it & 1;
-            const float* demod = demod_base + buf * CF_ND;
-            mbar_wait(&demod_full[buf], (it >> 1) & 1);
+    int service = 0;                      // which warp serves this tile: it mod 6
+    for (uint32_t it = 0; it < n_mine; ++it) {
+        const int st = it % CF_STAGES;
+        const uint32_t tile = first + it * gridDim.x;
+        const uint32_t s = tile / tps;
+        const uint32_t t = tile - s * tps;
+        const int buf = it & 1;
+        float* demod = demod_base + buf * CF_ND;
+        const bool serving = (warp == service);
+        // frames 0..4 go to the five other warps in rotation order
+        int slot = warp - service - 1;
+        if (slot < 0) slot += CF_WARPS;
 
-            // ---- half-band #1 (audio_main.c:133); work index 0 <-> 2*n0 - 10 ----
-            for (int m = lane; m < CF_NW; m += 32) {
-                const float* x = demod + 2 * m + 12;
-                work[m] = halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&demod_empty[buf]);
-            // ---- half-band #2 (audio_main.c:139) ----
-            float* out = p.audio + (int64_t) s * p.audio_stride + (int64_t) t * 128;
+        mbar_wait(&full[st], (it / CF_STAGES) & 1);
+        const uint8_t* in = ring + st * CF_STAGE_BYTES;
+
+        // ---- discriminator share: 3 chunks of 31 outputs (lane 0 only supplies phase[j-1]);
+        //      demod[buf] must have been drained by the audio job of tile it - 2 ----
+        if (it >= 2) mbar_wait(&demod_empty[buf], ((it - 2) >> 1) & 1);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const float* x = work + 2 * (32 * r + lane) + 10;
-                out[32 * r + lane] = halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
-            }
-            __syncwarp();       // work[] is rewritten by the next tile
+        for (int c3 = 0; c3 < 3; ++c3) {
+            const int j = 31 * (warp + CF_WARPS * c3) + lane;
+            uint32_t ure = CIC_MAGIC_BITS, uim = CIC_MAGIC_BITS;
+            if (j < CF_ND) cic10_sum(reinterpret_cast<const uint32_t*>(in + j * 20), ure, uim);
+            const float ph = atan2_approx_dev(__uint_as_float(uim) - CIC_MAGIC, __uint_as_float(ure) - CIC_MAGIC);
+            const float prev = __shfl_up_sync(0xffffffffu, ph, 1);
+            if (lane > 0 && j < CF_ND) demod[j] = fm_limit(ph, prev);     // demod[0] is never read
         }
-    } else {
-        // =============================== spectrum warps ===============================
-        float2* xch = reinterpret_cast<float2*>(xch_base + warp * FFT1024_XCH_BYTES);
-        float2 tw[32];
-        fft1024_load_twiddles(p.twiddle, lane, tw);
 
-        for (uint32_t it = 0; it < n_mine; ++it) {
-            const int st = it % CF_STAGES;
-            const uint32_t tile = first + it * gridDim.x;
-            const uint32_t s = tile / tps;
-            const uint32_t t = tile - s * tps;
-            const int buf = it & 1;
-            float* demod = demod_base + buf * CF_ND;
-            mbar_wait(&full[st], (it / CF_STAGES) & 1);
-            const uint8_t* in = ring + st * CF_STAGE_BYTES;
-
-            // ---- discriminator share of this warp: chunks of 31 outputs (lane 0 only supplies
-            //      phase[j-1]); demod[buf] must have been drained by the audio warp (tile it - 2) ----
-            if (it >= 2) mbar_wait(&demod_empty[buf], ((it - 2) >> 1) & 1);
-            for (int c = warp; c < 18; c += CF_FFT_WARPS) {
-                const int j = 31 * c + lane;
-                uint32_t ure = CIC_MAGIC_BITS, uim = CIC_MAGIC_BITS;
-                if (j < CF_ND) cic10_sum(reinterpret_cast<const uint32_t*>(in + j * 20), ure, uim);
-                const float ph = atan2_approx_dev(__uint_as_float(uim) - CIC_MAGIC, __uint_as_float(ure) - CIC_MAGIC);
-                const float prev = __shfl_up_sync(0xffffffffu, ph, 1);
-                if (lane > 0 && j < CF_ND) demod[j] = fm_limit(ph, prev);     // demod[0] is never read
-            }
-
+        if (!serving) {
             c64 a[32];
-            fft1024_load<false>(reinterpret_cast<const uint16_t*>(in + 2 * CF_HIST + 2048 * warp), nullptr, lane, a);
+            fft1024_load<false>(reinterpret_cast<const uint16_t*>(in + 2 * CF_HIST + 2048 * slot), nullptr, lane, a);
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&empty[st]);
                 mbar_arrive(&demod_full[buf]);
             }
-
             float pw[32];
             fft1024_core<true>(a, tw, xch, lane, pw);
             // DC-position patch (spectrum.c:30-33): display index 512 takes display index 511's value
             const float left = __shfl_sync(0xffffffffu, pw[31], 31);
             if (lane == 0) pw[0] = left;
-            float* out = p.db + ((size_t) s * tps * 5 + (size_t) t * 5 + warp) * 1024 + lane;
+            float* out = p.db + ((size_t) s * tps * 5 + (size_t) t * 5 + slot) * 1024 + lane;
 #pragma unroll
             for (int k2 = 0; k2 < 32; ++k2)
                 __stcs(out + fft1024_col(k2), fmaf(DB_PER_LOG2, lg2_ftz(pw[k2]), p.dboff));
+        } else {
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty[st]);
+                mbar_arrive(&demod_full[buf]);
+                // keep the ring full: tile it + STAGES - 1 goes into the stage tile it - 1 used
+                if (it + CF_STAGES - 1 < n_mine) {
+                    if (it > 0) mbar_wait(&empty[(it - 1) % CF_STAGES], ((it - 1) / CF_STAGES) & 1);
+                    issue(it + CF_STAGES - 1);
+                }
+            }
+            __syncwarp();
+            if (it > 0) audio_job(it - 1);
         }
+        service = (service + 1 == CF_WARPS) ? 0 : service + 1;
     }
+    // the last tile's audio: the warp that would serve tile n_mine
+    if (n_mine > 0 && warp == service) audio_job(n_mine - 1);
 }
 
 }  // namespace

@@ -215,3 +215,21 @@ def test_full_size_parseval_checksum(pkg, cuda):
     assert torch.equal(power[:, 512], power[:, 511])
     # a checksum of checksums over all frames, in float64
     assert abs(got.sum().item() / want.sum().item() - 1) < 1e-7
+
+
+def test_db_only_matches_all_outputs(pkg, cuda, po, synth):
+    """Requesting only the dB output must give the same bits as requesting everything, for odd
+    row counts and several streams (the outputs are written by separate store loops)."""
+    torch = cuda
+    for n_streams, n_frames in ((1, 1), (1, 7), (3, 5), (4, 16), (5, 333)):
+        ring = pkg.StreamRing(n_streams, 1024 * n_frames + 8)
+        iqs = np.stack([synth.s2_tones(1024 * n_frames + 8, seed=200 + s) for s in range(n_streams)])
+        ring.load(iqs)
+        plan = pkg.SpectrumPlan(1024)
+        fast = plan.exec(ring.batch, db=True)["db"]
+        both = plan.exec(ring.batch, db=True, power=True)
+        torch.cuda.synchronize()
+        assert fast.shape == (n_streams, n_frames, 1024)
+        assert torch.equal(fast, both["db"])
+        for s in range(min(n_streams, 2)):
+            check_db(fast[s].cpu().numpy(), po.Spectrum(1024).rows(iqs[s]))
