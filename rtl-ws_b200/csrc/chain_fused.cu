@@ -6,10 +6,10 @@
 //
 // Tile = 5120 samples = lcm(1024, 4 * 10): 5 frames and 128 audio samples, plus the FM
 // branch's 320-sample history (32 decimated samples) in front: 10880 bytes, fetched by one
-// TMA bulk copy into a three-deep ring with full/empty mbarriers.  A CTA is 6 symmetric warps
+// TMA bulk copy into a four-deep ring with full/empty mbarriers.  A CTA is 6 symmetric warps
 // that never meet at a block barrier.  For every tile each warp
 //   - does a third of a sixth... precisely 3 of the tile's 18 discriminator chunks (CIC sums
-//     with dp4a, atan2_approx, difference + limiter -> demod[], double buffered),
+//     with dp4a, atan2_approx, difference + limiter -> demod[], four buffers deep),
 //   - and 5 of the 6 warps unpack one frame each into registers, release the stage, run the
 //     32x32 two-pass transform, |X|^2, dB and store 4 KB of spectrum;
 //   - the sixth warp (rotating: tile index mod 6) is the tile's service warp: it re-arms the
@@ -28,15 +28,16 @@ namespace {
 
 constexpr int CF_WARPS = 6;
 constexpr int CF_THREADS = CF_WARPS * 32;
-constexpr int CF_STAGES = 3;
+constexpr int CF_STAGES = 4;
+constexpr int CF_DBUF = 4;                          // demod[] / work[] buffers: tiles a fast warp may run ahead
 constexpr int CF_TILE = 5120;                       // samples
 constexpr int CF_HIST = 320;                        // samples of history in front of a tile
 constexpr int CF_STAGE_BYTES = 2 * (CF_TILE + CF_HIST);   // 10880
 constexpr int CF_ND = (CF_TILE + CF_HIST) / 10;     // 544 decimated samples per tile
 constexpr int CF_NW = 2 * 128 + 10;                 // 266 first-stage outputs per tile
 constexpr int CF_WORK = 272;                        // CF_NW padded
-constexpr int CF_SMEM = CF_STAGES * CF_STAGE_BYTES + CF_WARPS * FFT1024_XCH_BYTES + 2 * CF_ND * 4 + 2 * CF_WORK * 4 +
-                        (2 * CF_STAGES + 4) * 8;
+constexpr int CF_SMEM = CF_STAGES * CF_STAGE_BYTES + CF_WARPS * FFT1024_XCH_BYTES + CF_DBUF * CF_ND * 4 +
+                        CF_DBUF * CF_WORK * 4 + (2 * CF_STAGES + 2 * CF_DBUF) * 8;
 
 struct ChainParams {
     const uint8_t* iq;             // stream 0, first sample of the batch (history lies before it)
@@ -59,12 +60,12 @@ __global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainP
     uint8_t* ring = smem;
     uint8_t* xch_base = smem + CF_STAGES * CF_STAGE_BYTES;
     float2* xch = reinterpret_cast<float2*>(xch_base + warp * FFT1024_XCH_BYTES);
-    float* demod_base = reinterpret_cast<float*>(xch_base + CF_WARPS * FFT1024_XCH_BYTES);   // [2][CF_ND]
-    float* work_base = demod_base + 2 * CF_ND;                                               // [2][CF_WORK]
-    uint64_t* full = reinterpret_cast<uint64_t*>(work_base + 2 * CF_WORK);
+    float* demod_base = reinterpret_cast<float*>(xch_base + CF_WARPS * FFT1024_XCH_BYTES);   // [CF_DBUF][CF_ND]
+    float* work_base = demod_base + CF_DBUF * CF_ND;                                         // [CF_DBUF][CF_WORK]
+    uint64_t* full = reinterpret_cast<uint64_t*>(work_base + CF_DBUF * CF_WORK);
     uint64_t* empty = full + CF_STAGES;
-    uint64_t* demod_full = empty + CF_STAGES;       // [2]
-    uint64_t* demod_empty = demod_full + 2;         // [2]
+    uint64_t* demod_full = empty + CF_STAGES;       // [CF_DBUF]
+    uint64_t* demod_empty = demod_full + CF_DBUF;   // [CF_DBUF]
 
     const uint32_t tps = (uint32_t) p.tiles_per_stream;
     const uint32_t total_tiles = (uint32_t) p.n_streams * tps;
@@ -85,10 +86,10 @@ __global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainP
         const uint32_t tile = first + it * gridDim.x;
         const uint32_t s = tile / tps;
         const uint32_t t = tile - s * tps;
-        const int buf = it & 1;
+        const int buf = it % CF_DBUF;
         const float* demod = demod_base + buf * CF_ND;
         float* work = work_base + buf * CF_WORK;
-        mbar_wait(&demod_full[buf], (it >> 1) & 1);
+        mbar_wait(&demod_full[buf], (it / CF_DBUF) & 1);
         for (int m = lane; m < CF_NW; m += 32) {            // work index 0 <-> 2*n0 - 10
             const float* x = demod + 2 * m + 12;
             work[m] = halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainP
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], CF_WARPS);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < CF_DBUF; ++i) {
             mbar_init(&demod_full[i], CF_WARPS);
             mbar_init(&demod_empty[i], 1);
         }
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainP
         const uint32_t tile = first + it * gridDim.x;
         const uint32_t s = tile / tps;
         const uint32_t t = tile - s * tps;
-        const int buf = it & 1;
+        const int buf = it % CF_DBUF;
         float* demod = demod_base + buf * CF_ND;
         const bool serving = (warp == service);
         // frames 0..4 go to the five other warps in rotation order
@@ -137,8 +138,8 @@ __global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainP
         const uint8_t* in = ring + st * CF_STAGE_BYTES;
 
         // ---- discriminator share: 3 chunks of 31 outputs (lane 0 only supplies phase[j-1]);
-        //      demod[buf] must have been drained by the audio job of tile it - 2 ----
-        if (it >= 2) mbar_wait(&demod_empty[buf], ((it - 2) >> 1) & 1);
+        //      demod[buf] must have been drained by the audio job of tile it - CF_DBUF ----
+        if (it >= CF_DBUF) mbar_wait(&demod_empty[buf], ((it - CF_DBUF) / CF_DBUF) & 1);
 #pragma unroll
         for (int c3 = 0; c3 < 3; ++c3) {
             const int j = 31 * (warp + CF_WARPS * c3) + lane;
