@@ -264,7 +264,8 @@ def main():
     pkg.init(local_rank)
 
     L = (args.samples_per_stream // TILE) * TILE
-    my_streams = [s for s in range(args.streams) if s % world == rank]
+    sharding = pkg.sharding
+    my_streams = sharding.streams_for_rank(args.streams, world, rank)
     n_local = len(my_streams)
 
     ring = pkg.StreamRing(n_local, L)
@@ -274,7 +275,6 @@ def main():
     db = torch.empty((n_local, L // 1024, 1024), dtype=torch.float32, device=device)
     audio = torch.empty((n_local, L // 40), dtype=torch.float32, device=device)
     avg_u8 = torch.zeros((n_local, 1024), dtype=torch.uint8, device=device)
-    gathered = [torch.zeros_like(avg_u8) for _ in range(world)] if (world > 1 and rank == 0) else None
     avg_plan = pkg.SpectrumPlan(1024, K=6)
     stream = torch.cuda.current_stream()
 
@@ -291,8 +291,8 @@ def main():
             kern_events.append((e0, e1))
         avg_plan.exec(ring.batch, n_rows=1, db=False, db_u8=True, out={"db_u8": avg_u8.view(n_local, 1, 1024)})
         ring.carry()                                                      # stream state for the next batch
-        if world > 1:
-            dist.gather(avg_u8, gathered, dst=0)
+        if world > 1:      # the one exchange: averaged u8 spectra of all 256 streams to rank 0 (NCCL)
+            sharding.gather_spectra(avg_u8, args.streams, world, rank, dist=dist)
 
     def sync_all():
         torch.cuda.synchronize()
