@@ -18,29 +18,52 @@ def local_count(n_streams: int, world: int, rank: int) -> int:
     return len(range(rank, n_streams, world))
 
 
-def gather_spectra(local, n_streams: int, world: int, rank: int, dist=None, dst: int = 0):
-    """Gather per-stream rows to `dst` and put them back in global stream order.
+class SpectraGatherer:
+    """Gather of per-stream rows (e.g. [n_local, 1024] u8 spectra) to rank `dst`, with every buffer
+    allocated once: a step costs exactly one collective and no allocation or reordering kernel.
 
-    local: [n_local, ...] tensor of this rank's streams (ascending global id).  Ranks may own
-    different counts when world does not divide n_streams; rows are padded to the maximum for
-    the collective.  Returns the [n_streams, ...] tensor on `dst`, None elsewhere."""
-    import torch
-    if world == 1:
-        return local
-    n_max = local_count(n_streams, world, 0)
-    if local.shape[0] < n_max:
-        pad = torch.zeros((n_max - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        local = torch.cat([local, pad], dim=0)
-    local = local.contiguous()
-    parts = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
-    dist.gather(local, parts, dst=dst)
-    if rank != dst:
-        return None
-    out = torch.empty((n_streams,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    for r in range(world):
-        ids = streams_for_rank(n_streams, world, r)
-        out[ids] = parts[r][:len(ids)]
-    return out
+    The receive buffer is rank-major, [world, n_max, ...]; `ordered()` puts it in global stream
+    order on demand (stream s sits at [s mod world, s div world])."""
+
+    def __init__(self, n_streams: int, world: int, rank: int, row_shape, dtype, device, dist=None, dst: int = 0):
+        import torch
+        self.n_streams, self.world, self.rank, self.dist, self.dst = n_streams, world, rank, dist, dst
+        self.n_local = local_count(n_streams, world, rank)
+        self.n_max = local_count(n_streams, world, 0)
+        row_shape = tuple(row_shape)
+        # the send buffer kernels write into directly (padded to n_max rows for the collective)
+        self.send = torch.zeros((self.n_max,) + row_shape, dtype=dtype, device=device)
+        self.local = self.send[:self.n_local]
+        self.recv = None
+        self.parts = None
+        if world > 1 and rank == dst:
+            self.recv = torch.zeros((world, self.n_max) + row_shape, dtype=dtype, device=device)
+            self.parts = list(self.recv.unbind(0))
+
+    def gather(self):
+        if self.world > 1:
+            self.dist.gather(self.send, self.parts, dst=self.dst)
+
+    def ordered(self):
+        """[n_streams, ...] in global stream order (on dst; None elsewhere)."""
+        import torch
+        if self.world == 1:
+            return self.local
+        if self.rank != self.dst:
+            return None
+        out = torch.empty((self.n_streams,) + tuple(self.recv.shape[2:]), dtype=self.recv.dtype, device=self.recv.device)
+        for r in range(self.world):
+            ids = streams_for_rank(self.n_streams, self.world, r)
+            out[ids] = self.recv[r, :len(ids)]
+        return out
+
+
+def gather_spectra(local, n_streams: int, world: int, rank: int, dist=None, dst: int = 0):
+    """One-shot convenience over SpectraGatherer: [n_local, ...] -> [n_streams, ...] on dst."""
+    g = SpectraGatherer(n_streams, world, rank, local.shape[1:], local.dtype, local.device, dist=dist, dst=dst)
+    g.local.copy_(local)
+    g.gather()
+    return g.ordered()
 
 
 def max_over_ranks(value: float, world: int, dist=None, device="cpu") -> float:
