@@ -23,6 +23,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libref_rtlws.so")
 REF_BENCH = os.path.join(HERE, "_ref", "ref_bench")
+# the reference's own glue (cbb_main.c, audio_main.c, signal_source.c) linked against the PRODUCT
+# library instead of the reference's spectrum.o / resample.o / rf_decimator.o
+DROPIN_SO = os.path.join(HERE, "_ref", "libdropin_rtlws.so")
+PRODUCT_SO = os.path.join(os.path.dirname(HERE), "rtl-ws_b200", "libb200sdr.so")
 
 HALF_BAND_N = 11
 
@@ -277,12 +281,15 @@ def chain_run(iq: np.ndarray, chunk: int = 131072, sample_rate: float = 2048000.
 class Ref:
     """A private copy of libref_rtlws.so: audio_main.c / cbb_main.c statics start from zero."""
 
+    SO = REF_SO
+
     def __init__(self):
-        if not have_ref():
-            raise FileNotFoundError(REF_SO)
+        if not os.path.exists(self.SO):
+            raise FileNotFoundError(self.SO)
+        self._preload()
         fd, self._tmp = tempfile.mkstemp(prefix="libref_rtlws_", suffix=".so")
         os.close(fd)
-        shutil.copyfile(REF_SO, self._tmp)
+        shutil.copyfile(self.SO, self._tmp)
         lib = C.CDLL(self._tmp)
         os.unlink(self._tmp)
         self.lib = lib
@@ -309,6 +316,9 @@ class Ref:
         lib.rf_decimator_set_parameters.argtypes = [C.c_void_p, C.c_double, C.c_int]
         lib.rf_decimator_decimate_cmplx_u8.argtypes = [C.c_void_p, _u8p, C.c_int]
         lib.rf_decimator_free.argtypes = [C.c_void_p]
+
+    def _preload(self):
+        pass
 
     # spectrum.c ------------------------------------------------------------------
     def spectrum_rows(self, iq: np.ndarray, N: int, hop: int | None = None, K: int = 1,
@@ -400,3 +410,20 @@ class Ref:
         nd, na = self.lib.ref_fm_n_decimated(), self.lib.ref_fm_n_audio()
         return dict(payload=payload[:k].copy(), power=power[:k].copy(), count=count[:k].copy(),
                     decimated=dec[:nd].copy(), audio=audio[:na].copy())
+
+
+class DropIn(Ref):
+    """The drop-in proof: the SAME harness and the reference's unmodified glue, but spectrum_*,
+    rf_decimator_*, cic_decimate and halfband_decimate resolve to libb200sdr.so (the GPU).
+    Only cbb_run / fm_chain / spectrum_rows make sense here (ref_atan2_approx etc. still exist)."""
+
+    SO = DROPIN_SO
+
+    def _preload(self):
+        # the private copy lives in a temp dir, so its $ORIGIN rpath no longer finds the product
+        # library: load it first, by path, into the global namespace
+        C.CDLL(PRODUCT_SO, mode=C.RTLD_GLOBAL)
+
+
+def have_dropin() -> bool:
+    return os.path.exists(DROPIN_SO) and os.path.exists(PRODUCT_SO)

@@ -32,9 +32,7 @@ __global__ void k(float* out, float a0, unsigned long long* cycles)
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[i]) : "r"(y[i + 8]), "r"(it));
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[i + 8]) : "r"(y[i]), "r"(it));
             } else if (MODE == 3) {         // +8 shared loads
-                float v;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned) (((threadIdx.x + i * 32 + it) & 1023) * 4)));
-                acc += v;
+                acc += sm[(threadIdx.x + i * 32 + it) & 1023];
             } else if (MODE == 4) {         // +8 scalar FADD (same pipe)
                 asm volatile("add.f32 %0, %0, %1;" : "+f"(acc) : "f"(a0));
             }
