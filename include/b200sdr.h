@@ -148,6 +148,32 @@ void b200_session_destroy(b200_session* s);
 void b200_session_reset(b200_session* s);      /* all streams back to stream start */
 int b200_session_chain(b200_session* s, const uint8_t* h_iq, int64_t n_samples, int gain_db,
                        float* h_db, float* h_audio);
+/* ---- push-style streaming: what a signal_source callback calls ------------------------------
+ *
+ * signal_source.c:29-35 hands every registered callback a BORROWED buffer of cmplx_u8 and its
+ * length (signal_source.h:7).  b200_stream_push is that callback's body: it copies the samples
+ * into the stream's pinned host slot and returns; whenever a slot holds `batch_samples`
+ * (a multiple of 5120, e.g. the reference's 204800-sample block, rf_decimator.c:65-66) it is
+ * submitted asynchronously -- H2D copy, the fused chain kernel, history carry, D2H copies --
+ * on one of the library's CUDA streams.  Finished batches are handed to the sinks from inside
+ * push / poll / flush, on the calling thread, in order:
+ *   spectrum sink: n_frames rows of 1024 float dB (display order) starting at frame first_frame;
+ *   audio sink:    n floats at fs/40 starting at audio sample first_sample.
+ * The pointers passed to a sink are valid until it returns.  Batching is aligned to stream
+ * start, so results do not depend on the chunking of the pushes (as with rf_decimator).
+ */
+typedef struct b200_stream b200_stream;
+typedef void (*b200_spectrum_sink)(void* user, int stream, int64_t first_frame, int n_frames, const float* db);
+typedef void (*b200_audio_sink)(void* user, int stream, int64_t first_sample, int n, const float* audio);
+b200_stream* b200_stream_create(int n_streams, int64_t batch_samples, int gain_db);
+void b200_stream_destroy(b200_stream* s);
+void b200_stream_set_sinks(b200_stream* s, b200_spectrum_sink spectrum_sink, b200_audio_sink audio_sink, void* user);
+/* samples: len interleaved (re, im) byte pairs, i.e. a `const cmplx_u8*` */
+int b200_stream_push(b200_stream* s, int stream, const uint8_t* samples, int len);
+int b200_stream_poll(b200_stream* s);           /* deliver whatever has finished, never blocks */
+int b200_stream_flush(b200_stream* s);          /* wait for and deliver every submitted batch */
+int64_t b200_stream_pending_samples(const b200_stream* s, int stream);   /* buffered, not yet a whole batch */
+
 void* b200_host_alloc(uint64_t bytes);          /* pinned host memory */
 void b200_host_free(void* p);
 

@@ -8,7 +8,7 @@ module name ``rtl_ws_b200``.
 """
 from . import binding, sharding, synth  # noqa: F401
 from .binding import (  # noqa: F401
-    B200Error, SpectrumPlan, StreamRing, Session, RfDecimator, CicDelayLine,
+    B200Error, SpectrumPlan, StreamRing, Session, PushStream, RfDecimator, CicDelayLine,
     fm_exec, chain_exec, init, lib, launch_count,
     spectrum_alloc, spectrum_free, spectrum_add_cmplx_u8, spectrum_add_cmplx_s32, spectrum_add_real_f32,
     cic_decimate, halfband_decimate,

@@ -28,6 +28,8 @@ EXPORTED_SYMBOLS = [
     "b200_fm_history_samples", "b200_fm_history_reset", "b200_fm_history_carry", "b200_fm_exec",
     "b200_chain_exec",
     "b200_session_create", "b200_session_destroy", "b200_session_reset", "b200_session_chain",
+    "b200_stream_create", "b200_stream_destroy", "b200_stream_set_sinks", "b200_stream_push", "b200_stream_poll",
+    "b200_stream_flush", "b200_stream_pending_samples",
     "b200_host_alloc", "b200_host_free",
     "spectrum_alloc", "spectrum_add_cmplx_u8", "spectrum_add_cmplx_s32", "spectrum_add_real_f32", "spectrum_free",
     "cic_decimate", "halfband_decimate",
@@ -50,6 +52,8 @@ class CicDelayLine(C.Structure):
 
 
 RF_CALLBACK = C.CFUNCTYPE(None, C.POINTER(CmplxS32), C.c_int)
+SPECTRUM_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_float))
+AUDIO_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_float))
 
 _lib = None
 
@@ -85,6 +89,16 @@ def lib() -> C.CDLL:
     L.b200_session_destroy.argtypes = [vp]
     L.b200_session_reset.argtypes = [vp]
     L.b200_session_chain.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.b200_stream_create.restype = vp
+    L.b200_stream_create.argtypes = [i32, i64, i32]
+    L.b200_stream_destroy.argtypes = [vp]
+    L.b200_stream_set_sinks.restype = None
+    L.b200_stream_set_sinks.argtypes = [vp, SPECTRUM_SINK, AUDIO_SINK, vp]
+    L.b200_stream_push.argtypes = [vp, i32, vp, i32]
+    L.b200_stream_poll.argtypes = [vp]
+    L.b200_stream_flush.argtypes = [vp]
+    L.b200_stream_pending_samples.restype = i64
+    L.b200_stream_pending_samples.argtypes = [vp, i32]
     L.b200_host_alloc.restype = vp
     L.b200_host_alloc.argtypes = [u64]
     L.b200_host_free.argtypes = [vp]
@@ -311,6 +325,49 @@ class Session:
             return C.c_void_p(x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data)
         _check(lib().b200_session_chain(self.h, hp(h_iq), n_samples, gain_db, hp(h_db), hp(h_audio)),
                "b200_session_chain")
+
+
+class PushStream:
+    """b200_stream_*: signal_source-style pushes in, spectra and audio out through sinks."""
+
+    def __init__(self, n_streams: int, batch_samples: int, gain_db: int = 0):
+        _torch()
+        self.n_streams, self.batch = n_streams, batch_samples
+        self.h = lib().b200_stream_create(n_streams, batch_samples, gain_db)
+        if not self.h:
+            raise B200Error(f"b200_stream_create: {last_error()}")
+        self.spectra = [[] for _ in range(n_streams)]      # (first_frame, [n_frames, 1024] copy)
+        self.audio = [[] for _ in range(n_streams)]        # (first_sample, [n] copy)
+
+        def on_spectrum(user, stream, first, n, ptr):
+            self.spectra[stream].append((first, np.ctypeslib.as_array(ptr, shape=(n, 1024)).copy()))
+
+        def on_audio(user, stream, first, n, ptr):
+            self.audio[stream].append((first, np.ctypeslib.as_array(ptr, shape=(n,)).copy()))
+
+        self._cb = (SPECTRUM_SINK(on_spectrum), AUDIO_SINK(on_audio))
+        lib().b200_stream_set_sinks(self.h, self._cb[0], self._cb[1], None)
+
+    def push(self, stream: int, samples: np.ndarray) -> None:
+        samples = np.ascontiguousarray(samples, dtype=np.uint8)
+        _check(lib().b200_stream_push(self.h, stream, samples.ctypes.data, samples.size // 2), "b200_stream_push")
+
+    def poll(self) -> None:
+        _check(lib().b200_stream_poll(self.h), "b200_stream_poll")
+
+    def flush(self) -> None:
+        _check(lib().b200_stream_flush(self.h), "b200_stream_flush")
+
+    def pending(self, stream: int) -> int:
+        return int(lib().b200_stream_pending_samples(self.h, stream))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_stream_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 # --------------------------------------------------------------------------------------

@@ -1,0 +1,241 @@
+// stream.cu -- b200_stream_*: the push-style entry point a signal_source callback calls
+// (signal_source.h:7 `void (*)(const cmplx_u8*, int)`, fan-out at signal_source.c:29-35).
+//
+// Each of n independent dongle streams owns two pinned host slots of `batch_samples`
+// (the "pinned host rings" of the north star).  b200_stream_push copies the callback's
+// borrowed buffer (librtlsdr recycles it) into the current slot; a full slot is submitted
+// without blocking: cudaMemcpyAsync to the stream's device row [history | batch], the fused
+// chain kernel for that row, the history carry, and asynchronous copies of the dB rows and
+// the audio back into pinned result buffers -- all on one of a small pool of CUDA streams,
+// so batches of different dongles overlap.  Results are handed to the caller's sinks from
+// b200_stream_push / _poll / _flush on the calling thread (no hidden threads), in submission
+// order per stream.  Re-blocking is aligned to stream start like rf_decimator.c:88-115, so
+// results do not depend on how the source chunks the samples.
+#include <string.h>
+
+#include <vector>
+
+#include "b200_common.cuh"
+
+using namespace b200;
+
+namespace b200 {
+int launch_fm_history_carry(uint8_t* iq, int64_t stride, int n_streams, int64_t n_samples, int R, cudaStream_t stream);
+int launch_fm_history_reset(uint8_t* iq, int64_t stride, int n_streams, int R, cudaStream_t stream);
+int fm_history_samples(int R);
+}  // namespace b200
+
+namespace {
+constexpr int ST_TILE = 5120;
+constexpr int ST_R = 10;
+constexpr int ST_SLOTS = 2;
+constexpr int ST_LANES = 4;
+}  // namespace
+
+struct b200_stream {
+    int n_streams;
+    int64_t batch;                 // samples per batch (multiple of 5120)
+    int gain_db;
+    int hist;                      // samples
+    int64_t row_bytes;             // device row pitch: history + batch
+    uint8_t* d_rows;               // [n_streams][ST_SLOTS? no: one row per stream][row_bytes]
+    float* d_db;                   // [n_streams][batch]
+    float* d_audio;                // [n_streams][batch / 40]
+    uint8_t* h_in;                 // pinned [n_streams][ST_SLOTS][2 * batch]
+    float* h_db;                   // pinned [n_streams][ST_SLOTS][batch]
+    float* h_audio;                // pinned [n_streams][ST_SLOTS][batch / 40]
+    cudaStream_t lanes[ST_LANES];
+    struct PerStream {
+        int64_t fill;              // samples in the current slot
+        int slot;                  // slot being filled
+        int64_t batches_submitted;
+        int64_t batches_delivered;
+        cudaEvent_t done[ST_SLOTS];
+        bool in_flight[ST_SLOTS];
+    };
+    std::vector<PerStream> st;
+    b200_spectrum_sink spectrum_sink;
+    b200_audio_sink audio_sink;
+    void* user;
+};
+
+static void stream_deliver(b200_stream* s, int i, bool block)
+{
+    b200_stream::PerStream& p = s->st[i];
+    while (p.batches_delivered < p.batches_submitted) {
+        const int slot = (int) (p.batches_delivered % ST_SLOTS);
+        if (!p.in_flight[slot]) break;
+        if (block) {
+            if (cudaEventSynchronize(p.done[slot]) != cudaSuccess) break;
+        } else if (cudaEventQuery(p.done[slot]) != cudaSuccess) {
+            break;
+        }
+        const int64_t b = p.batches_delivered;
+        const size_t off = ((size_t) i * ST_SLOTS + slot);
+        if (s->spectrum_sink)
+            s->spectrum_sink(s->user, i, b * (s->batch / 1024), (int) (s->batch / 1024), s->h_db + off * (size_t) s->batch);
+        if (s->audio_sink)
+            s->audio_sink(s->user, i, b * (s->batch / 40), (int) (s->batch / 40), s->h_audio + off * (size_t) (s->batch / 40));
+        p.in_flight[slot] = false;
+        ++p.batches_delivered;
+    }
+}
+
+static int stream_submit(b200_stream* s, int i)
+{
+    b200_stream::PerStream& p = s->st[i];
+    const int slot = p.slot;
+    const size_t off = ((size_t) i * ST_SLOTS + slot);
+    cudaStream_t lane = s->lanes[i % ST_LANES];
+    uint8_t* d_batch = s->d_rows + (size_t) i * (size_t) s->row_bytes + 2 * (size_t) s->hist;
+    float* d_db = s->d_db + (size_t) i * (size_t) s->batch;
+    float* d_audio = s->d_audio + (size_t) i * (size_t) (s->batch / 40);
+    B200_CUDA_TRY(cudaMemcpyAsync(d_batch, s->h_in + off * 2 * (size_t) s->batch, 2 * (size_t) s->batch,
+                                  cudaMemcpyHostToDevice, lane));
+    int rc = b200_chain_exec(d_batch, s->row_bytes, 1, s->batch, s->gain_db, d_db, d_audio, s->batch / 40, nullptr, 0, lane);
+    if (rc) return rc;
+    rc = launch_fm_history_carry(d_batch, s->row_bytes, 1, s->batch, ST_R, lane);
+    if (rc) return rc;
+    B200_CUDA_TRY(cudaMemcpyAsync(s->h_db + off * (size_t) s->batch, d_db, sizeof(float) * (size_t) s->batch,
+                                  cudaMemcpyDeviceToHost, lane));
+    B200_CUDA_TRY(cudaMemcpyAsync(s->h_audio + off * (size_t) (s->batch / 40), d_audio,
+                                  sizeof(float) * (size_t) (s->batch / 40), cudaMemcpyDeviceToHost, lane));
+    B200_CUDA_TRY(cudaEventRecord(p.done[slot], lane));
+    p.in_flight[slot] = true;
+    ++p.batches_submitted;
+    p.slot = (slot + 1) % ST_SLOTS;
+    p.fill = 0;
+    return B200_OK;
+}
+
+extern "C" {
+
+b200_stream* b200_stream_create(int n_streams, int64_t batch_samples, int gain_db)
+{
+    if (n_streams < 1 || batch_samples < ST_TILE || batch_samples % ST_TILE != 0) {
+        set_error("stream: batch_samples must be a positive multiple of %d", ST_TILE);
+        return nullptr;
+    }
+    b200_stream* s = new b200_stream();
+    s->n_streams = n_streams;
+    s->batch = batch_samples;
+    s->gain_db = gain_db;
+    s->hist = fm_history_samples(ST_R);
+    s->row_bytes = 2 * ((int64_t) s->hist + batch_samples);
+    s->d_rows = nullptr;
+    s->d_db = nullptr;
+    s->d_audio = nullptr;
+    s->h_in = nullptr;
+    s->h_db = nullptr;
+    s->h_audio = nullptr;
+    s->spectrum_sink = nullptr;
+    s->audio_sink = nullptr;
+    s->user = nullptr;
+    for (int i = 0; i < ST_LANES; ++i) s->lanes[i] = nullptr;
+    const size_t ns = (size_t) n_streams;
+    bool ok = cudaMalloc(&s->d_rows, ns * (size_t) s->row_bytes) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_db, sizeof(float) * ns * (size_t) batch_samples) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_audio, sizeof(float) * ns * (size_t) (batch_samples / 40)) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&s->h_in, ns * ST_SLOTS * 2 * (size_t) batch_samples, cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&s->h_db, sizeof(float) * ns * ST_SLOTS * (size_t) batch_samples, cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&s->h_audio, sizeof(float) * ns * ST_SLOTS * (size_t) (batch_samples / 40), cudaHostAllocDefault) == cudaSuccess;
+    for (int i = 0; ok && i < ST_LANES; ++i) ok = cudaStreamCreateWithFlags(&s->lanes[i], cudaStreamNonBlocking) == cudaSuccess;
+    s->st.resize(ns);
+    for (size_t i = 0; i < ns; ++i) {
+        s->st[i].fill = 0;
+        s->st[i].slot = 0;
+        s->st[i].batches_submitted = 0;
+        s->st[i].batches_delivered = 0;
+        for (int k = 0; k < ST_SLOTS; ++k) {
+            s->st[i].done[k] = nullptr;
+            s->st[i].in_flight[k] = false;
+            if (ok) ok = cudaEventCreateWithFlags(&s->st[i].done[k], cudaEventDisableTiming) == cudaSuccess;
+        }
+    }
+    if (ok)
+        ok = launch_fm_history_reset(s->d_rows + 2 * (size_t) s->hist, s->row_bytes, n_streams, ST_R, s->lanes[0]) == B200_OK &&
+             cudaStreamSynchronize(s->lanes[0]) == cudaSuccess;
+    if (!ok) {
+        set_error("stream: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        b200_stream_destroy(s);
+        return nullptr;
+    }
+    return s;
+}
+
+void b200_stream_destroy(b200_stream* s)
+{
+    if (s == nullptr) return;
+    for (int i = 0; i < ST_LANES; ++i)
+        if (s->lanes[i]) {
+            cudaStreamSynchronize(s->lanes[i]);
+            cudaStreamDestroy(s->lanes[i]);
+        }
+    for (auto& p : s->st)
+        for (int k = 0; k < ST_SLOTS; ++k)
+            if (p.done[k]) cudaEventDestroy(p.done[k]);
+    if (s->d_rows) cudaFree(s->d_rows);
+    if (s->d_db) cudaFree(s->d_db);
+    if (s->d_audio) cudaFree(s->d_audio);
+    if (s->h_in) cudaFreeHost(s->h_in);
+    if (s->h_db) cudaFreeHost(s->h_db);
+    if (s->h_audio) cudaFreeHost(s->h_audio);
+    delete s;
+}
+
+void b200_stream_set_sinks(b200_stream* s, b200_spectrum_sink spectrum_sink, b200_audio_sink audio_sink, void* user)
+{
+    s->spectrum_sink = spectrum_sink;
+    s->audio_sink = audio_sink;
+    s->user = user;
+}
+
+int b200_stream_push(b200_stream* s, int stream, const uint8_t* samples, int len)
+{
+    if (s == nullptr || stream < 0 || stream >= s->n_streams || len < 0 || (len > 0 && samples == nullptr)) {
+        set_error("stream push: bad arguments");
+        return B200_ERR_ARG;
+    }
+    b200_stream::PerStream& p = s->st[stream];
+    const uint8_t* src = samples;
+    int64_t remaining = len;
+    while (remaining > 0) {
+        // the slot about to be written must have been delivered (two batches in flight at most)
+        if (p.fill == 0 && p.in_flight[p.slot]) stream_deliver(s, stream, true);
+        const int64_t room = s->batch - p.fill;
+        const int64_t n = remaining < room ? remaining : room;
+        uint8_t* dst = s->h_in + ((size_t) stream * ST_SLOTS + p.slot) * 2 * (size_t) s->batch + 2 * (size_t) p.fill;
+        memcpy(dst, src, 2 * (size_t) n);
+        src += 2 * n;
+        p.fill += n;
+        remaining -= n;
+        if (p.fill == s->batch) {
+            const int rc = stream_submit(s, stream);
+            if (rc) return rc;
+        }
+    }
+    stream_deliver(s, stream, false);
+    return B200_OK;
+}
+
+int b200_stream_poll(b200_stream* s)
+{
+    if (s == nullptr) return B200_ERR_ARG;
+    for (int i = 0; i < s->n_streams; ++i) stream_deliver(s, i, false);
+    return B200_OK;
+}
+
+int b200_stream_flush(b200_stream* s)
+{
+    if (s == nullptr) return B200_ERR_ARG;
+    for (int i = 0; i < s->n_streams; ++i) stream_deliver(s, i, true);
+    return B200_OK;
+}
+
+int64_t b200_stream_pending_samples(const b200_stream* s, int stream)
+{
+    if (s == nullptr || stream < 0 || stream >= s->n_streams) return B200_ERR_ARG;
+    return s->st[stream].fill;
+}
+
+}  // extern "C"

@@ -151,3 +151,38 @@ def test_session_host_buffers(pkg, cuda, po, synth):
     with pytest.raises(pkg.B200Error):
         sess.chain(h_iq, 5000, h_db, h_audio)
     sess.close()
+
+
+def test_push_stream_like_a_signal_source_callback(pkg, cuda, po, synth):
+    """Three dongles pushing 131072-sample source buffers (signal_source.c:31) in round robin;
+    batches of one reference block (204800 samples); sinks receive everything in order."""
+    n_streams, batch = 3, 204800
+    n = 3 * batch + 50_000                      # the last 50 000 samples stay pending
+    iq = [synth.s3_fm(n, seed=300 + s) for s in range(n_streams)]
+    ps = pkg.PushStream(n_streams, batch)
+    for pos in range(0, n, 131072):
+        for s in range(n_streams):
+            ps.push(s, iq[s][pos:pos + 131072])
+    ps.flush()
+    for s in range(n_streams):
+        assert ps.pending(s) == 50_000
+        assert [f for f, _ in ps.spectra[s]] == [0, 200, 400]
+        assert [f for f, _ in ps.audio[s]] == [0, 5120, 10240]
+        db = np.concatenate([r for _, r in ps.spectra[s]])
+        audio = np.concatenate([a for _, a in ps.audio[s]])
+        rows = po.Spectrum(1024).rows(iq[s][:3 * batch])
+        ok = rows > 1e-6 * rows.mean(axis=1, keepdims=True)
+        assert np.abs(db[ok] - 10 * np.log10(rows[ok])).max() <= 0.01
+        _, want = po.chain_run(iq[s][:3 * batch])
+        assert np.abs(audio - want).max() <= 1e-4
+    # chunking independence: one stream, odd pushes
+    ps2 = pkg.PushStream(1, batch)
+    for pos in range(0, n, 7777):
+        ps2.push(0, iq[0][pos:pos + 7777])
+    ps2.flush()
+    a2 = np.concatenate([a for _, a in ps2.audio[0]])
+    assert np.array_equal(a2, np.concatenate([a for _, a in ps.audio[0]]))
+    with pytest.raises(pkg.B200Error):
+        pkg.PushStream(1, 1000)
+    ps.close()
+    ps2.close()
