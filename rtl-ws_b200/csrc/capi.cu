@@ -43,6 +43,7 @@ int sm_count()
 // launchers implemented next to their kernels
 int launch_spectrum1024(const SpecParams& p, cudaStream_t stream);
 int launch_spectrum_generic(const SpecParams& p, int N, int kind, cudaStream_t stream);
+int launch_spectrum_mx1024(const SpecParams& p, int N, cudaStream_t stream);
 int launch_fm_chain(const FmParams& p, cudaStream_t stream);
 int launch_fm_history_carry(uint8_t* iq, int64_t stride, int n_streams, int64_t n_samples, int R, cudaStream_t stream);
 int launch_fm_history_reset(uint8_t* iq, int64_t stride, int n_streams, int R, cudaStream_t stream);
@@ -60,10 +61,27 @@ struct b200_spectrum_plan {
     int window;
     int gain_db;
     float db_offset;
-    float2* d_twiddle;
+    float2* d_twiddle;             // N-point table
+    float2* d_twiddle1024;         // 1024-point table (N = 2048 / 4096 / 8192 run M branches of 1024)
     float* d_window;
     int device;
 };
+
+static float2* upload_twiddles(int N)
+{
+    std::vector<float2> tw((size_t) N);
+    for (int k = 0; k < N; ++k) {
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double) k / (long double) N;
+        tw[k] = make_float2((float) cosl(a), (float) sinl(a));
+    }
+    float2* d = nullptr;
+    if (cudaMalloc(&d, sizeof(float2) * (size_t) N) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, tw.data(), sizeof(float2) * (size_t) N, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(d);
+        return nullptr;
+    }
+    return d;
+}
 
 extern "C" {
 
@@ -135,13 +153,10 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
         delete pl;
         return nullptr;
     }
-    std::vector<float2> tw((size_t) N);
-    for (int k = 0; k < N; ++k) {
-        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double) k / (long double) N;
-        tw[k] = make_float2((float) cosl(a), (float) sinl(a));
-    }
-    if (cudaMalloc(&pl->d_twiddle, sizeof(float2) * (size_t) N) != cudaSuccess ||
-        cudaMemcpy(pl->d_twiddle, tw.data(), sizeof(float2) * (size_t) N, cudaMemcpyHostToDevice) != cudaSuccess) {
+    pl->d_twiddle1024 = nullptr;
+    pl->d_twiddle = upload_twiddles(N);
+    if (pl->d_twiddle != nullptr && (N == 2048 || N == 4096 || N == 8192)) pl->d_twiddle1024 = upload_twiddles(1024);
+    if (pl->d_twiddle == nullptr || ((N == 2048 || N == 4096 || N == 8192) && pl->d_twiddle1024 == nullptr)) {
         set_error("spectrum plan: twiddle upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         if (pl->d_twiddle) cudaFree(pl->d_twiddle);
         delete pl;
@@ -168,6 +183,7 @@ void b200_spectrum_plan_destroy(b200_spectrum_plan* plan)
 {
     if (plan == nullptr) return;
     if (plan->d_twiddle) cudaFree(plan->d_twiddle);
+    if (plan->d_twiddle1024) cudaFree(plan->d_twiddle1024);
     if (plan->d_window) cudaFree(plan->d_window);
     delete plan;
 }
@@ -209,6 +225,7 @@ static int spectrum_exec_kind(b200_spectrum_plan* plan, const void* d_in, int64_
     p.db_u8 = d_db_u8;
     p.db_offset = plan->db_offset;
     p.twiddle = plan->d_twiddle;
+    p.twiddle_n = nullptr;
     p.window = plan->d_window;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     if (kind == 0 && plan->N == 1024) {
@@ -217,6 +234,15 @@ static int spectrum_exec_kind(b200_spectrum_plan* plan, const void* d_in, int64_
             return B200_ERR_ALIGN;
         }
         return launch_spectrum1024(p, stream);
+    }
+    if (kind == 0 && plan->d_twiddle1024 != nullptr) {
+        if ((reinterpret_cast<uintptr_t>(d_in) & 15) != 0 || (stream_stride_bytes & 15) != 0) {
+            set_error("spectrum exec: IQ pointer and stream stride must be 16-byte aligned");
+            return B200_ERR_ALIGN;
+        }
+        p.twiddle = plan->d_twiddle1024;
+        p.twiddle_n = plan->d_twiddle;
+        return launch_spectrum_mx1024(p, plan->N, stream);
     }
     return launch_spectrum_generic(p, plan->N, kind, stream);
 }

@@ -53,16 +53,16 @@ __device__ __forceinline__ void fft1024_load(const uint16_t* in16, const float* 
     }
 }
 
-// Both passes.  `a` as left by fft1024_load.  On return pw[k2] = |X[lane + 32 * k2]|^2 * 2^30
-// (raw power).  xch: this warp's exchange tile.  The caller must __syncwarp() between the last
-// read of the frame bytes and anything that overwrites them; xch reuse across frames is
-// ordered by the __syncwarp() before the writes below.
+// Both passes.  `a` as left by fft1024_load (or any loader that fills a[bitrev<32>(n1)] with
+// sample 32*n1 + lane).  On return b[k2] = X[lane + 32 * k2].  xch: this warp's exchange tile.
+// The caller must __syncwarp() between the last read of the frame bytes and anything that
+// overwrites them; xch reuse across frames is ordered by the __syncwarp() before the writes.
 // The inter-pass twiddles W_1024^(n2*k1) are applied on the READ side (lane = k1, register
 // n2 -- the table is symmetric, so the same lane-private tw[] serves) fused into pass 2's first
 // butterfly stage.
 template <bool BIASED>
-__device__ __forceinline__ void fft1024_core(c64 (&a)[32], const float2 (&tw)[32], float2* xch, int lane,
-                                             float (&pw)[32])
+__device__ __forceinline__ void fft1024_transform(c64 (&a)[32], const float2 (&tw)[32], float2* xch, int lane,
+                                                  c64 (&b)[32])
 {
     fft_dit32<false>(a, tw);
     if (BIASED) a[0] = csub(a[0], cpack(269484032.0f, 269484032.0f));   // 32 * (2^23 + 2^15)
@@ -70,7 +70,6 @@ __device__ __forceinline__ void fft1024_core(c64 (&a)[32], const float2 (&tw)[32
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1) reinterpret_cast<c64*>(xch)[k1 * FFT1024_XCH_STRIDE + lane] = a[k1];
     __syncwarp();
-    c64 b[32];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
         const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&xch[lane * FFT1024_XCH_STRIDE + 2 * m]);
@@ -78,6 +77,15 @@ __device__ __forceinline__ void fft1024_core(c64 (&a)[32], const float2 (&tw)[32
         b[bitrev<32>(2 * m + 1)] = v.y;
     }
     fft_dit32<true>(b, tw);
+}
+
+// transform + |X|^2:  pw[k2] = |X[lane + 32 * k2]|^2 * 2^30 (raw power)
+template <bool BIASED>
+__device__ __forceinline__ void fft1024_core(c64 (&a)[32], const float2 (&tw)[32], float2* xch, int lane,
+                                             float (&pw)[32])
+{
+    c64 b[32];
+    fft1024_transform<BIASED>(a, tw, xch, lane, b);
 #pragma unroll
     for (int k2 = 0; k2 < 32; ++k2) {
         float re, im;

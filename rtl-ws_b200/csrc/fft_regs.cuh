@@ -203,6 +203,22 @@ __device__ __forceinline__ void fft_dit32(c64 (&a)[32], const float2 (&tw)[32])
     }
 }
 
+// In-place forward DIT FFT of R <= 16 points, no pre-twiddles.  Input a[p] = x[bitrev<R>(p)],
+// output natural order.
+template <int R>
+__device__ __forceinline__ void fft_dit_small(c64 (&a)[R])
+{
+    static_assert(R == 2 || R == 4 || R == 8 || R == 16, "small register FFT sizes");
+#pragma unroll
+    for (int half = 1; half < R; half <<= 1) {
+#pragma unroll
+        for (int g = 0; g < R; g += 2 * half) {
+#pragma unroll
+            for (int k = 0; k < half; ++k) dit_butterfly(a[g + k], a[g + k + half], k * (16 / half));
+        }
+    }
+}
+
 // In-place forward DIF FFT of R points held in registers; result index bitrev<R>(p) is in a[p].
 template <int R>
 __device__ __forceinline__ void fft_dif(c64 (&a)[R])
