@@ -26,8 +26,9 @@ namespace b200 {
 
 namespace {
 
-constexpr int CF_WARPS = 6;
-constexpr int CF_THREADS = CF_WARPS * 32;
+constexpr int CF_WARPS = 6;                         // warps per group: 5 transforms + 1 service per tile
+constexpr int CF_GROUPS = 2;                        // independent groups per CTA (see kernel comment)
+constexpr int CF_THREADS = CF_GROUPS * CF_WARPS * 32;
 constexpr int CF_STAGES = 4;
 constexpr int CF_DBUF = 4;                          // demod[] / work[] buffers: tiles a fast warp may run ahead
 constexpr int CF_TILE = 5120;                       // samples
@@ -36,8 +37,10 @@ constexpr int CF_STAGE_BYTES = 2 * (CF_TILE + CF_HIST);   // 10880
 constexpr int CF_ND = (CF_TILE + CF_HIST) / 10;     // 544 decimated samples per tile
 constexpr int CF_NW = 2 * 128 + 10;                 // 266 first-stage outputs per tile
 constexpr int CF_WORK = 272;                        // CF_NW padded
-constexpr int CF_SMEM = CF_STAGES * CF_STAGE_BYTES + CF_WARPS * FFT1024_XCH_BYTES + CF_DBUF * CF_ND * 4 +
-                        CF_DBUF * CF_WORK * 4 + (2 * CF_STAGES + 2 * CF_DBUF) * 8;
+constexpr int CF_GROUP_SMEM = CF_STAGES * CF_STAGE_BYTES + CF_WARPS * FFT1024_XCH_BYTES + CF_DBUF * CF_ND * 4 +
+                              CF_DBUF * CF_WORK * 4 + (2 * CF_STAGES + 2 * CF_DBUF) * 8;
+static_assert(CF_GROUP_SMEM % 128 == 0, "group shared memory must keep the TMA destinations 128-byte aligned");
+constexpr int CF_SMEM = CF_GROUPS * CF_GROUP_SMEM;
 
 struct ChainParams {
     const uint8_t* iq;             // stream 0, first sample of the batch (history lies before it)
@@ -51,12 +54,17 @@ struct ChainParams {
     const float2* twiddle;
 };
 
-__global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainParams p)
+// One CTA per SM holds TWO independent six-warp groups (own ring, own barriers, own tiles):
+// warps are assigned to the four schedulers by warp index mod 4, so a lone six-warp CTA would
+// load them 2-2-1-1 (and two such CTAs 4-4-2-2); twelve warps in one CTA land 3-3-3-3.
+__global__ void __launch_bounds__(CF_THREADS, 1) chain_fused_kernel(const ChainParams p)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem_all[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int warp = tid >> 5;
+    const int group = (tid >> 5) / CF_WARPS;
+    const int warp = (tid >> 5) % CF_WARPS;
+    uint8_t* smem = smem_all + group * CF_GROUP_SMEM;
     uint8_t* ring = smem;
     uint8_t* xch_base = smem + CF_STAGES * CF_STAGE_BYTES;
     float2* xch = reinterpret_cast<float2*>(xch_base + warp * FFT1024_XCH_BYTES);
@@ -69,11 +77,12 @@ __global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainP
 
     const uint32_t tps = (uint32_t) p.tiles_per_stream;
     const uint32_t total_tiles = (uint32_t) p.n_streams * tps;
-    const uint32_t first = blockIdx.x;
-    const uint32_t n_mine = first < total_tiles ? (total_tiles - first + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t first = blockIdx.x * CF_GROUPS + group;           // groups stride over tiles like CTAs would
+    const uint32_t stride = gridDim.x * CF_GROUPS;
+    const uint32_t n_mine = first < total_tiles ? (total_tiles - first + stride - 1) / stride : 0;
 
     auto issue = [&](uint32_t it) {
-        const uint32_t tile = first + it * gridDim.x;
+        const uint32_t tile = first + it * stride;
         const uint32_t s = tile / tps;
         const uint32_t t = tile - s * tps;
         const int st = it % CF_STAGES;
@@ -83,7 +92,7 @@ __global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainP
     };
     // the two half-band decimators of local tile `it` (audio_main.c:133,139); one warp
     auto audio_job = [&](uint32_t it) {
-        const uint32_t tile = first + it * gridDim.x;
+        const uint32_t tile = first + it * stride;
         const uint32_t s = tile / tps;
         const uint32_t t = tile - s * tps;
         const int buf = it % CF_DBUF;
@@ -104,7 +113,7 @@ __global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainP
         }
     };
 
-    if (tid == 0) {
+    if (warp == 0 && lane == 0) {
         for (int i = 0; i < CF_STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], CF_WARPS);
@@ -124,7 +133,7 @@ __global__ void __launch_bounds__(CF_THREADS, 2) chain_fused_kernel(const ChainP
     int service = 0;                      // which warp serves this tile: it mod 6
     for (uint32_t it = 0; it < n_mine; ++it) {
         const int st = it % CF_STAGES;
-        const uint32_t tile = first + it * gridDim.x;
+        const uint32_t tile = first + it * stride;
         const uint32_t s = tile / tps;
         const uint32_t t = tile - s * tps;
         const int buf = it % CF_DBUF;
@@ -219,7 +228,8 @@ int launch_chain_fused(const uint8_t* d_iq, int64_t stride, int n_streams, int64
     B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, chain_fused_kernel, CF_THREADS, CF_SMEM));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     int64_t grid = (int64_t) sm_count() * ctas_per_sm;
-    if (grid > total) grid = total;
+    const int64_t needed = (total + CF_GROUPS - 1) / CF_GROUPS;
+    if (grid > needed) grid = needed;
     chain_fused_kernel<<<(unsigned) grid, CF_THREADS, CF_SMEM, stream>>>(p);
     B200_LAUNCH_CHECK();
     return B200_OK;
