@@ -44,6 +44,7 @@ int sm_count()
 int launch_spectrum1024(const SpecParams& p, cudaStream_t stream);
 int launch_spectrum_generic(const SpecParams& p, int N, int kind, cudaStream_t stream);
 int launch_spectrum_mx1024(const SpecParams& p, int N, cudaStream_t stream);
+int launch_spectrum64k(const SpecParams& p, const Spec64kExtra& x, cudaStream_t stream);
 int launch_fm_chain(const FmParams& p, cudaStream_t stream);
 int launch_fm_history_carry(uint8_t* iq, int64_t stride, int n_streams, int64_t n_samples, int R, cudaStream_t stream);
 int launch_fm_history_reset(uint8_t* iq, int64_t stride, int n_streams, int R, cudaStream_t stream);
@@ -64,6 +65,7 @@ struct b200_spectrum_plan {
     float2* d_twiddle;             // N-point table
     float2* d_twiddle1024;         // 1024-point table (N = 2048 / 4096 / 8192 run M branches of 1024)
     float* d_window;
+    Spec64kExtra x64;              // N = 65536 only (all null otherwise)
     int device;
 };
 
@@ -154,9 +156,11 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
         return nullptr;
     }
     pl->d_twiddle1024 = nullptr;
+    memset(&pl->x64, 0, sizeof(pl->x64));
     pl->d_twiddle = upload_twiddles(N);
-    if (pl->d_twiddle != nullptr && (N == 2048 || N == 4096 || N == 8192)) pl->d_twiddle1024 = upload_twiddles(1024);
-    if (pl->d_twiddle == nullptr || ((N == 2048 || N == 4096 || N == 8192) && pl->d_twiddle1024 == nullptr)) {
+    const bool wants1024 = (N == 2048 || N == 4096 || N == 8192 || N == 65536);
+    if (pl->d_twiddle != nullptr && wants1024) pl->d_twiddle1024 = upload_twiddles(1024);
+    if (pl->d_twiddle == nullptr || (wants1024 && pl->d_twiddle1024 == nullptr)) {
         set_error("spectrum plan: twiddle upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         if (pl->d_twiddle) cudaFree(pl->d_twiddle);
         delete pl;
@@ -176,6 +180,34 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
             return nullptr;
         }
     }
+    if (N == 65536) {
+        // tables in the layout the four-step kernel reads coalesced, and its L2-resident scratch
+        std::vector<float2> trk((size_t) 64 * 1024);
+        for (int r = 0; r < 64; ++r)
+            for (int k = 0; k < 1024; ++k) {
+                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double) ((long long) r * k) / 65536.0L;
+                trk[(size_t) r * 1024 + k] = make_float2((float) cosl(a), (float) sinl(a));
+            }
+        bool ok = cudaMalloc((void**) &pl->x64.twiddle_rk, sizeof(float2) * trk.size()) == cudaSuccess &&
+                  cudaMemcpy((void*) pl->x64.twiddle_rk, trk.data(), sizeof(float2) * trk.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        if (ok && window == B200_WINDOW_HANN) {
+            std::vector<float> wrm((size_t) 65536);
+            for (int r = 0; r < 64; ++r)
+                for (int m = 0; m < 1024; ++m)
+                    wrm[(size_t) r * 1024 + m] = (float) (0.5L - 0.5L * cosl(2.0L * 3.14159265358979323846264338327950288L *
+                                                                             (long double) (64 * m + r) / 65536.0L));
+            ok = cudaMalloc((void**) &pl->x64.window_rm, sizeof(float) * wrm.size()) == cudaSuccess &&
+                 cudaMemcpy((void*) pl->x64.window_rm, wrm.data(), sizeof(float) * wrm.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+        pl->x64.scratch_ctas = sm_count();
+        ok = ok && cudaMalloc((void**) &pl->x64.scratch, sizeof(float2) * 65536 * (size_t) pl->x64.scratch_ctas) == cudaSuccess;
+        if (ok && K > 1) ok = cudaMalloc((void**) &pl->x64.acc, sizeof(float) * 65536 * (size_t) pl->x64.scratch_ctas) == cudaSuccess;
+        if (!ok) {
+            set_error("spectrum plan: 65536-point tables / scratch: %s", cudaGetErrorString(cudaGetLastError()));
+            b200_spectrum_plan_destroy(pl);
+            return nullptr;
+        }
+    }
     return pl;
 }
 
@@ -185,6 +217,10 @@ void b200_spectrum_plan_destroy(b200_spectrum_plan* plan)
     if (plan->d_twiddle) cudaFree(plan->d_twiddle);
     if (plan->d_twiddle1024) cudaFree(plan->d_twiddle1024);
     if (plan->d_window) cudaFree(plan->d_window);
+    if (plan->x64.twiddle_rk) cudaFree((void*) plan->x64.twiddle_rk);
+    if (plan->x64.window_rm) cudaFree((void*) plan->x64.window_rm);
+    if (plan->x64.scratch) cudaFree(plan->x64.scratch);
+    if (plan->x64.acc) cudaFree(plan->x64.acc);
     delete plan;
 }
 
@@ -242,6 +278,7 @@ static int spectrum_exec_kind(b200_spectrum_plan* plan, const void* d_in, int64_
         }
         p.twiddle = plan->d_twiddle1024;
         p.twiddle_n = plan->d_twiddle;
+        if (plan->N == 65536) return launch_spectrum64k(p, plan->x64, stream);
         return launch_spectrum_mx1024(p, plan->N, stream);
     }
     return launch_spectrum_generic(p, plan->N, kind, stream);

@@ -110,6 +110,38 @@ __host__ __device__ constexpr float sin32(int q)
     return cos32(q - 8);
 }
 
+// cos(2*pi*q/64), q = 0..16, for the 64-point transform of the four-step kernel
+__host__ __device__ constexpr float cos64_table(int q)
+{
+    return q == 0    ? 1.0f
+           : q == 1  ? 0.99518472667219688624f
+           : q == 2  ? 0.98078528040323044913f
+           : q == 3  ? 0.95694033573220886494f
+           : q == 4  ? 0.92387953251128675613f
+           : q == 5  ? 0.88192126434835502971f
+           : q == 6  ? 0.83146961230254523708f
+           : q == 7  ? 0.77301045336273696081f
+           : q == 8  ? 0.70710678118654752440f
+           : q == 9  ? 0.63439328416364549822f
+           : q == 10 ? 0.55557023301960222474f
+           : q == 11 ? 0.47139673682599764856f
+           : q == 12 ? 0.38268343236508977173f
+           : q == 13 ? 0.29028467725446236764f
+           : q == 14 ? 0.19509032201612826785f
+           : q == 15 ? 0.09801714032956060199f
+                     : 0.0f;
+}
+__host__ __device__ constexpr float cos64(int q)
+{
+    q &= 63;
+    if (q > 32) q = 64 - q;
+    return q <= 16 ? cos64_table(q) : -cos64_table(32 - q);
+}
+__host__ __device__ constexpr float sin64(int q)
+{
+    return cos64(q - 16);
+}
+
 template <int R>
 __host__ __device__ constexpr int bitrev(int i)
 {
@@ -199,6 +231,37 @@ __device__ __forceinline__ void fft_dit32(c64 (&a)[32], const float2 (&tw)[32])
         for (int g = 0; g < 32; g += 2 * half) {
 #pragma unroll
             for (int k = 0; k < half; ++k) dit_butterfly(a[g + k], a[g + k + half], k * (16 / half));
+        }
+    }
+}
+
+// DIT butterfly with twiddle exp(-2*pi*i*q/64), 0 <= q < 32 (same three-instruction form)
+__device__ __forceinline__ void dit_butterfly64(c64& u, c64& v, int q)
+{
+    if ((q & 1) == 0) {
+        dit_butterfly(u, v, q >> 1);
+        return;
+    }
+    float vr, vi;
+    cunpack(v, vr, vi);
+    const float c = cos64(q);
+    const float sn = sin64(q);
+    const c64 s = cfma2(v, cpack(c, c), cfma2(cpack(vi, -vr), cpack(sn, sn), u));
+    float sr, si;
+    cunpack(s, sr, si);
+    v = cfma2(u, cpack(2.0f, 2.0f), cpack(-sr, -si));
+    u = s;
+}
+
+// In-place forward DIT FFT of 64 points.  Input a[p] = x[bitrev<64>(p)], output natural order.
+__device__ __forceinline__ void fft_dit64(c64 (&a)[64])
+{
+#pragma unroll
+    for (int half = 1; half < 64; half <<= 1) {
+#pragma unroll
+        for (int g = 0; g < 64; g += 2 * half) {
+#pragma unroll
+            for (int k = 0; k < half; ++k) dit_butterfly64(a[g + k], a[g + k + half], k * (32 / half));
         }
     }
 }

@@ -1,0 +1,178 @@
+// spectrum64k.cu -- 65536-point power spectra (BASELINE config 4: wideband spectrogram,
+// Hann window, 50 % overlap), one CTA per frame, four-step through an L2-resident scratch
+// (sm_100a).
+//
+// 65536 = 64 x 1024, decimation in time by 64:
+//   X[k + 1024 q] = sum_{r<64} W_64^(r q) * ( W_N^(r k) * F_r[k] ),   F_r = FFT_1024( x[64 m + r] ).
+// A CTA (8 warps, one per SM) owns one frame at a time:
+//   0. the 128 KB of IQ bytes are copied into shared memory with 128-bit loads; every 128-byte
+//      row (one m, all 64 r) is word-swizzled by (m mod 32) so that the stride-128-byte reads
+//      of a polyphase branch hit 32 different banks;
+//   1. warp w runs the 32x32 register transform (fft1024_warp.cuh) on branches r = w, w+8, ...,
+//      multiplies by W_N^(r k) (table stored [r][k], read coalesced) and writes Z[r][k] to this
+//      CTA's 512 KB slice of a global scratch that stays in the 126 MB L2;
+//   2. block barrier; thread t takes k = t, t+256, t+512, t+768: 64 coalesced loads of Z[.][k],
+//      a 64-point FFT in registers, |X|^2, K-frame accumulation with the cumulative
+//      DC-position patch (spectrum.c:30-33), dB / power / u8, coalesced stores.
+// Arithmetic per frame as in spectrum1024.cu (spectrum.c:15-58, cbb_main.c:112-128); the window
+// (an extension; the reference is rectangular) is read from a table stored [r][m].
+#include "b200_common.cuh"
+#include "fft1024_warp.cuh"
+#include "spectrum_kernels.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int N64K = 65536;
+constexpr int S64_THREADS = 256;
+constexpr int S64_WARPS = 8;
+constexpr int S64_FRAME_BYTES = 2 * N64K;                                  // 131072
+constexpr int S64_SMEM = S64_FRAME_BYTES + S64_WARPS * FFT1024_XCH_BYTES + 16;
+
+template <bool WINDOW, bool MULTI>
+__global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecParams p, const Spec64kExtra x)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    uint32_t* frame32 = reinterpret_cast<uint32_t*>(smem);                 // [1024 rows][32 words], swizzled
+    float2* xch = reinterpret_cast<float2*>(smem + S64_FRAME_BYTES + warp * FFT1024_XCH_BYTES);
+    float* dc_slot = reinterpret_cast<float*>(smem + S64_FRAME_BYTES + S64_WARPS * FFT1024_XCH_BYTES);
+
+    c64* Z = reinterpret_cast<c64*>(x.scratch) + (size_t) blockIdx.x * N64K;     // [64][1024]
+    float* acc = x.acc + (size_t) blockIdx.x * N64K;                              // [65536], MULTI only
+
+    const int64_t total = (int64_t) p.n_streams * p.n_rows;
+    const int K = MULTI ? p.K : 1;
+    const float dboff = p.db_offset - 16.0f * DB_PER_LOG2;
+
+    float2 tw[32];
+    fft1024_load_twiddles(p.twiddle, lane, tw);
+
+    auto emit = [&](size_t row_base, int bin, float pw) {
+        const int col = (bin + N64K / 2) & (N64K - 1);
+        const float db = fmaf(DB_PER_LOG2, lg2_ftz(pw), dboff);
+        if (p.db) __stcs(p.db + row_base + col, db);
+        if (p.power) __stcs(p.power + row_base + col, pw * FFT1024_POWER_SCALE);
+        if (p.db_u8) {
+            int m = __float2int_rz(db);
+            m = m < 0 ? 0 : (m > 255 ? 255 : m);
+            p.db_u8[row_base + col] = (uint8_t) m;
+        }
+    };
+
+    for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+        const int64_t s = item / p.n_rows;
+        const int64_t row = item - s * p.n_rows;
+        const size_t row_base = (size_t) item * N64K;
+        float dcacc = 0.0f;
+
+        for (int j = 0; j < K; ++j) {
+            // ---- 0. frame -> shared memory, rows word-swizzled by (m mod 32) ----
+            const uint4* src = reinterpret_cast<const uint4*>(p.iq + s * p.stream_stride_bytes +
+                                                              2 * (row * p.row_hop + (int64_t) j * p.hop));
+#pragma unroll 4
+            for (int i = tid; i < S64_FRAME_BYTES / 16; i += S64_THREADS) {
+                const uint4 v = __ldg(src + i);
+                const int m = i >> 3;
+                const int w0 = (i & 7) * 4;
+                uint32_t* dst = frame32 + m * 32;
+                const int sw = m & 31;
+                dst[(w0 + 0) ^ sw] = v.x;
+                dst[(w0 + 1) ^ sw] = v.y;
+                dst[(w0 + 2) ^ sw] = v.z;
+                dst[(w0 + 3) ^ sw] = v.w;
+            }
+            __syncthreads();
+
+            // ---- 1. polyphase branches r = warp, warp + 8, ... ----
+            for (int r = warp; r < 64; r += S64_WARPS) {
+                c64 a[32];
+                {
+                    const c64 bias1 = cpack(8421376.0f, 8421376.0f);        // 2^23 + 256 * 128
+                    const uint8_t* fb = reinterpret_cast<const uint8_t*>(frame32);
+#pragma unroll
+                    for (int n1 = 0; n1 < 32; ++n1) {
+                        const int m = 32 * n1 + lane;                       // m mod 32 == lane
+                        const uint32_t v = *reinterpret_cast<const uint16_t*>(fb + m * 128 + (((r >> 1) ^ lane) << 2) + ((r & 1) << 1));
+                        const int q = bitrev<32>(n1);
+                        a[q] = cpack(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7504)),
+                                     __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7514)));
+                        if (WINDOW) {
+                            const float w = __ldg(&x.window_rm[r * 1024 + m]);
+                            a[q] = cmul2(csub(a[q], bias1), cpack(w, w));
+                        }
+                    }
+                }
+                c64 b[32];
+                fft1024_transform<!WINDOW>(a, tw, xch, lane, b);
+                const float2* twr = x.twiddle_rk + r * 1024;
+                c64* zr = Z + r * 1024;
+#pragma unroll
+                for (int k2 = 0; k2 < 32; ++k2) {
+                    const int k = lane + 32 * k2;
+                    c64 z = b[k2];
+                    if (r > 0) {
+                        const float2 w = __ldg(&twr[k]);
+                        z = cmul(z, w.x, w.y);
+                    }
+                    zr[k] = z;
+                }
+            }
+            __syncthreads();          // Z[.][.] of this frame is complete and visible to the CTA
+
+            // ---- 2. 64-point transforms across r for k = tid + 256 g ----
+            for (int g = 0; g < 4; ++g) {
+                const int k = tid + 256 * g;
+                c64 z[64];
+#pragma unroll
+                for (int r = 0; r < 64; ++r) z[bitrev<64>(r)] = Z[r * 1024 + k];
+                fft_dit64(z);
+#pragma unroll
+                for (int q = 0; q < 64; ++q) {
+                    float re, im;
+                    cunpack(z[q], re, im);
+                    const float pw = fmaf(re, re, im * im);
+                    const int bin = k + 1024 * q;
+                    if (MULTI) {
+                        acc[bin] = (j == 0 ? 0.0f : acc[bin]) + pw;
+                    } else if (bin != 0) {
+                        emit(row_base, bin, pw);
+                    }
+                    if (g == 3 && q == 63) dcacc = fmaf((float) (K - j), pw, dcacc);     // bin N-1 lives in thread 255
+                }
+            }
+            if (j == K - 1 && tid == S64_THREADS - 1) *dc_slot = dcacc;
+            __syncthreads();          // frame32 / Z are rewritten by the next frame; dc_slot is visible
+        }
+
+        // spectrum.c:30-33: the DC position takes the (cumulative) value of its left neighbour, bin N-1
+        if (!MULTI) {
+            if (tid == 0) emit(row_base, 0, *dc_slot);
+        } else {
+            const float dc = *dc_slot;
+            for (int bin = tid; bin < N64K; bin += S64_THREADS) emit(row_base, bin, bin == 0 ? dc : acc[bin]);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+int launch_spectrum64k(const SpecParams& p, const Spec64kExtra& x, cudaStream_t stream)
+{
+    const int64_t total = (int64_t) p.n_streams * p.n_rows;
+    if (total == 0) return B200_OK;
+    auto kern = p.K > 1 ? (p.window ? spectrum64k_kernel<true, true> : spectrum64k_kernel<false, true>)
+                        : (p.window ? spectrum64k_kernel<true, false> : spectrum64k_kernel<false, false>);
+    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S64_SMEM));
+    int64_t grid = x.scratch_ctas;
+    if (grid > total) grid = total;
+    kern<<<(unsigned) grid, S64_THREADS, S64_SMEM, stream>>>(p, x);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+}  // namespace b200

@@ -161,10 +161,24 @@ def test_goldens_n4096_n65536(pkg, cuda, synth):
     iq = synth.s2_tones(65536, N=65536, seed=int(g["seed"]))
     out = run_plan(pkg, cuda, iq, N=65536)
     check_power(out["power"][0], g["rows_k1"])
-    # wideband spectrogram shape: 65536-point Hann frames at 50% overlap
-    iq = synth.s2_tones(65536 * 3, N=65536, seed=5)
-    out = run_plan(pkg, cuda, iq, N=65536, hop=32768, window=pkg.WINDOW_HANN)
-    assert out["power"].shape == (1, 5, 65536)
+
+
+def test_wideband_spectrogram_65536_hann_overlap(pkg, cuda, po, synth):
+    """BASELINE config 4: 65536-point Hann frames at 50 % overlap, two streams; plus K = 2 rows."""
+    iqs = np.stack([synth.s2_tones(65536 * 3, N=65536, seed=5 + s) for s in range(2)])
+    out = run_plan(pkg, cuda, iqs, N=65536, hop=32768, window=pkg.WINDOW_HANN)
+    assert out["power"].shape == (2, 5, 65536)
+    for s in range(2):
+        want = po.Spectrum(65536, window=synth.hann(65536)).rows(iqs[s], hop=32768)
+        check_power(out["power"][s], want)
+        check_db(out["db"][s], want)
+        assert np.array_equal(out["power"][s].argmax(axis=1), want.argmax(axis=1))
+    out = run_plan(pkg, cuda, iqs, N=65536, hop=32768, K=2, window=pkg.WINDOW_HANN)
+    for s in range(2):
+        want = po.Spectrum(65536, window=synth.hann(65536)).rows(iqs[s], hop=32768, K=2)
+        check_power(out["power"][s], want)
+    out = run_plan(pkg, cuda, iqs[0], N=65536, K=3)
+    check_power(out["power"][0], po.Spectrum(65536).rows(iqs[0], K=3))
 
 
 def test_cs32_and_rf32_inputs(pkg, cuda, po):

@@ -35,12 +35,20 @@ db6 = torch.empty((S, L // 6144, 1024), dtype=torch.float32, device="cuda")
 plan4k = pkg.SpectrumPlan(4096)
 db4k = torch.empty((S, L // 4096, 4096), dtype=torch.float32, device="cuda")
 
+plan64k = pkg.SpectrumPlan(65536, hop=32768, window=pkg.WINDOW_HANN)
+rows64k = plan64k.rows(L)
+db64k = torch.empty((S, rows64k, 65536), dtype=torch.float32, device="cuda")
+plan2k = pkg.SpectrumPlan(2048)
+db2k = torch.empty((S, L // 2048, 2048), dtype=torch.float32, device="cuda")
+
 cases = {
     "spectrum1024_db": (lambda: plan.exec(ring.batch, db=True, out=out), 6.0),
     "spectrum1024_k6_db": (lambda: plan6.exec(ring.batch, db=True, out={"db": db6}), 2.0 + 4.0 / 6),
     "fm_chain": (lambda: pkg.fm_exec(ring, audio=audio), 2.1),
     "chain_fused": (lambda: pkg.chain_exec(ring, db=db, audio=audio), 6.1),
     "spectrum4096_db": (lambda: plan4k.exec(ring.batch, db=True, out={"db": db4k}), 6.0),
+    "spectrum2048_db": (lambda: plan2k.exec(ring.batch, db=True, out={"db": db2k}), 6.0),
+    "spectrum65536_hann_50pct": (lambda: plan64k.exec(ring.batch, db=True, out={"db": db64k}), 10.0),
 }
 for name, (fn, bps) in cases.items():
     if args.only and args.only != name:
