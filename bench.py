@@ -178,12 +178,12 @@ def run_ref_bench(n_streams: int, samples_per_stream: int, workers: int, mode: s
     shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     path = os.path.join(shm, f"b200sdr_refbench_{os.getpid()}.bin")
     try:
-        unique = [pkg.synth.s3_fm(samples_per_stream, seed=1000 + s) for s in range(min(n_streams, 16))]
+        n_unique = min(n_streams, 16)          # 16 distinct captures, reused round robin (timing is data-independent)
         with open(path, "wb") as f:
-            for s in range(n_streams):          # 16 distinct captures, repeated (timing is data-independent)
-                unique[s % len(unique)].tofile(f)
-        res = subprocess.run([po.REF_BENCH, path, str(n_streams), str(samples_per_stream), str(workers), mode],
-                             capture_output=True, text=True, timeout=900)
+            for s in range(n_unique):
+                pkg.synth.s3_fm(samples_per_stream, seed=1000 + s).tofile(f)
+        res = subprocess.run([po.REF_BENCH, path, str(n_streams), str(samples_per_stream), str(workers), mode,
+                              str(n_unique)], capture_output=True, text=True, timeout=900)
         if res.returncode != 0:
             return None
         return json.loads(res.stdout.strip().splitlines()[-1])
@@ -196,9 +196,8 @@ def cpu_sample_shape(cpu_seconds: float, workers: int):
     """A bounded sample of the workload: whole streams of 1 s (2 048 000 samples), enough of them for
     ~cpu_seconds of CPU work per worker at ~20 Msamples/s/core."""
     per_stream = FS
-    streams_per_worker = max(1, int(round(cpu_seconds * 20e6 / per_stream)))
-    n_streams = min(N_STREAMS * 4, workers * streams_per_worker)
-    return n_streams, per_stream
+    streams_per_worker = max(1, int(round(cpu_seconds * 45e6 / per_stream)))      # ~45-55 Msamples/s/core measured
+    return workers * streams_per_worker, per_stream
 
 
 def reference_arm(args):

@@ -7,8 +7,10 @@
  * demodulator state in statics, so parallelism is one PROCESS per worker, each taking
  * whole streams (streams are independent).
  *
- *   ref_bench <iq_file> <n_streams> <samples_per_stream> <n_workers> <mode>
+ *   ref_bench <iq_file> <n_streams> <samples_per_stream> <n_workers> <mode> [unique]
  *       mode: chain | spectrum | fm
+ *       unique: the file holds this many distinct captures (default n_streams); stream s reads
+ *               capture s mod unique, so a long run does not need a multi-gigabyte file
  *
  * Per stream, in the reference's own granularity:
  *   - the stream arrives in 131072-sample source buffers (signal_source.c:29-31);
@@ -93,7 +95,7 @@ static void run_stream(const uint8_t* iq, int64_t n, int do_spec, int do_fm,
 int main(int argc, char** argv)
 {
     const char* path;
-    int n_streams, n_workers, w, do_spec, do_fm;
+    int n_streams, n_workers, w, do_spec, do_fm, unique;
     int64_t per_stream;
     int fd;
     struct stat st;
@@ -104,7 +106,7 @@ int main(int argc, char** argv)
 
     if (argc < 6)
     {
-        fprintf(stderr, "usage: %s <iq_file> <n_streams> <samples_per_stream> <n_workers> <chain|spectrum|fm>\n", argv[0]);
+        fprintf(stderr, "usage: %s <iq_file> <n_streams> <samples_per_stream> <n_workers> <chain|spectrum|fm> [unique]\n", argv[0]);
         return 2;
     }
     path = argv[1];
@@ -113,12 +115,14 @@ int main(int argc, char** argv)
     n_workers = atoi(argv[4]);
     do_spec = strcmp(argv[5], "fm") != 0;
     do_fm = strcmp(argv[5], "spectrum") != 0;
+    unique = argc > 6 ? atoi(argv[6]) : n_streams;
+    if (unique < 1 || unique > n_streams) unique = n_streams;
     if (n_workers < 1) n_workers = 1;
     if (n_workers > 1024) n_workers = 1024;
     if (n_workers > n_streams) n_workers = n_streams;
 
     fd = open(path, O_RDONLY);
-    if (fd < 0 || fstat(fd, &st) != 0 || st.st_size < (off_t) (2 * per_stream * n_streams))
+    if (fd < 0 || fstat(fd, &st) != 0 || st.st_size < (off_t) (2 * per_stream * unique))
     {
         fprintf(stderr, "ref_bench: cannot use %s\n", path);
         return 2;
@@ -148,12 +152,12 @@ int main(int argc, char** argv)
             /* touch this worker's input once so page faults are outside the timed region */
             for (s = w; s < n_streams; s += n_workers)
                 for (k = 0; k < 2 * per_stream; k += 4096)
-                    sink ^= iq[(size_t) s * 2 * per_stream + k];
+                    sink ^= iq[(size_t) (s % unique) * 2 * per_stream + k];
             __sync_fetch_and_add(&ctl->ready, 1);
             while (!ctl->go)
                 usleep(50);
             for (s = w; s < n_streams; s += n_workers)
-                run_stream(iq + (size_t) s * 2 * per_stream, per_stream, do_spec, do_fm,
+                run_stream(iq + (size_t) (s % unique) * 2 * per_stream, per_stream, do_spec, do_fm,
                            spect, db_out, audio_out, audio_cap, &cs);
             ctl->checksum[w] = cs;
             _exit(0);

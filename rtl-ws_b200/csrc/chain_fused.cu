@@ -35,9 +35,10 @@ constexpr int CF_TILE = 5120;                       // samples
 constexpr int CF_HIST = 320;                        // samples of history in front of a tile
 constexpr int CF_STAGE_BYTES = 2 * (CF_TILE + CF_HIST);   // 10880
 constexpr int CF_ND = (CF_TILE + CF_HIST) / 10;     // 544 decimated samples per tile
+constexpr int CF_ND_PAD = 576;                      // demod[] pitch: the 18 chunks of 31 cover indices up to 557
 constexpr int CF_NW = 2 * 128 + 10;                 // 266 first-stage outputs per tile
 constexpr int CF_WORK = 272;                        // CF_NW padded
-constexpr int CF_GROUP_SMEM = CF_STAGES * CF_STAGE_BYTES + CF_WARPS * FFT1024_XCH_BYTES + CF_DBUF * CF_ND * 4 +
+constexpr int CF_GROUP_SMEM = CF_STAGES * CF_STAGE_BYTES + CF_WARPS * FFT1024_XCH_BYTES + CF_DBUF * CF_ND_PAD * 4 +
                               CF_DBUF * CF_WORK * 4 + (2 * CF_STAGES + 2 * CF_DBUF) * 8;
 static_assert(CF_GROUP_SMEM % 128 == 0, "group shared memory must keep the TMA destinations 128-byte aligned");
 constexpr int CF_SMEM = CF_GROUPS * CF_GROUP_SMEM;
@@ -68,8 +69,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) chain_fused_kernel(const ChainP
     uint8_t* ring = smem;
     uint8_t* xch_base = smem + CF_STAGES * CF_STAGE_BYTES;
     float2* xch = reinterpret_cast<float2*>(xch_base + warp * FFT1024_XCH_BYTES);
-    float* demod_base = reinterpret_cast<float*>(xch_base + CF_WARPS * FFT1024_XCH_BYTES);   // [CF_DBUF][CF_ND]
-    float* work_base = demod_base + CF_DBUF * CF_ND;                                         // [CF_DBUF][CF_WORK]
+    float* demod_base = reinterpret_cast<float*>(xch_base + CF_WARPS * FFT1024_XCH_BYTES);   // [CF_DBUF][CF_ND_PAD]
+    float* work_base = demod_base + CF_DBUF * CF_ND_PAD;                                         // [CF_DBUF][CF_WORK]
     uint64_t* full = reinterpret_cast<uint64_t*>(work_base + CF_DBUF * CF_WORK);
     uint64_t* empty = full + CF_STAGES;
     uint64_t* demod_full = empty + CF_STAGES;       // [CF_DBUF]
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) chain_fused_kernel(const ChainP
         const uint32_t s = tile / tps;
         const uint32_t t = tile - s * tps;
         const int buf = it % CF_DBUF;
-        const float* demod = demod_base + buf * CF_ND;
+        const float* demod = demod_base + buf * CF_ND_PAD;
         float* work = work_base + buf * CF_WORK;
         mbar_wait(&demod_full[buf], (it / CF_DBUF) & 1);
         for (int m = lane; m < CF_NW; m += 32) {            // work index 0 <-> 2*n0 - 10
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) chain_fused_kernel(const ChainP
         const uint32_t s = tile / tps;
         const uint32_t t = tile - s * tps;
         const int buf = it % CF_DBUF;
-        float* demod = demod_base + buf * CF_ND;
+        float* demod = demod_base + buf * CF_ND_PAD;
         const bool serving = (warp == service);
         // frames 0..4 go to the five other warps in rotation order
         int slot = warp - service - 1;
@@ -152,11 +153,14 @@ __global__ void __launch_bounds__(CF_THREADS, 1) chain_fused_kernel(const ChainP
 #pragma unroll
         for (int c3 = 0; c3 < 3; ++c3) {
             const int j = 31 * (warp + CF_WARPS * c3) + lane;
-            uint32_t ure = CIC_MAGIC_BITS, uim = CIC_MAGIC_BITS;
-            if (j < CF_ND) cic10_sum(reinterpret_cast<const uint32_t*>(in + j * 20), ure, uim);
+            // straight-line on purpose (the three chunks interleave): the last chunk's lanes 17..31
+            // read up to 280 bytes past the stage -- still inside this group's shared memory -- and
+            // write demod[544..557], padding that is never read
+            uint32_t ure, uim;
+            cic10_sum(reinterpret_cast<const uint32_t*>(in + j * 20), ure, uim);
             const float ph = atan2_approx_dev(__uint_as_float(uim) - CIC_MAGIC, __uint_as_float(ure) - CIC_MAGIC);
             const float prev = __shfl_up_sync(0xffffffffu, ph, 1);
-            if (lane > 0 && j < CF_ND) demod[j] = fm_limit(ph, prev);     // demod[0] is never read
+            if (lane > 0) demod[j] = fm_limit(ph, prev);                   // demod[0] is never read
         }
 
         if (!serving) {

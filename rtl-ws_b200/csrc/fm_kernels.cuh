@@ -64,7 +64,10 @@ __device__ __forceinline__ float atan2_approx_dev(float y, float x)
     const float y2 = y * y;
     const bool lt = fabsf(y) < fabsf(x);
     const float den = fmaf(0.28f, lt ? y2 : x2, lt ? x2 : y2);
-    const float q = __fdividef(x * y, den);
+    // den is an exact non-negative integer-valued float (0 or >= 1): no denormal handling needed
+    float rden;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"(den));
+    const float q = (x * y) * rden;
     float r = lt ? (q + (x < 0.0f ? copysignf(pi, y) : 0.0f)) : (copysignf(pi_by_2, y) - q);
     return den == 0.0f ? 0.0f : r;
 }
