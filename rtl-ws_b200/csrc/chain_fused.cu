@@ -100,18 +100,13 @@ __global__ void __launch_bounds__(CF_THREADS, 1) chain_fused_kernel(const ChainP
         const float* demod = demod_base + buf * CF_ND_PAD;
         float* work = work_base + buf * CF_WORK;
         mbar_wait(&demod_full[buf], (it / CF_DBUF) & 1);
-        for (int m = lane; m < CF_NW; m += 32) {            // work index 0 <-> 2*n0 - 10
-            const float* x = demod + 2 * m + 12;
-            work[m] = halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
-        }
+        for (int m = lane; m < CF_NW; m += 32)              // work index 0 <-> 2*n0 - 10
+            work[m] = halfband_from(demod + 2 * m + 2);
         __syncwarp();
         if (lane == 0) mbar_arrive(&demod_empty[buf]);
         float* out = p.audio + (int64_t) s * p.audio_stride + (int64_t) t * 128;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const float* x = work + 2 * (32 * r + lane) + 10;
-            out[32 * r + lane] = halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
-        }
+        for (int r = 0; r < 4; ++r) out[32 * r + lane] = halfband_from(work + 2 * (32 * r + lane));
     };
 
     if (warp == 0 && lane == 0) {

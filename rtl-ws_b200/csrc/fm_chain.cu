@@ -131,18 +131,12 @@ __global__ void __launch_bounds__(FM_THREADS) fm_chain_kernel(const FmParams p, 
 
         // ---- phase 2: half-band #1 (audio_main.c:133); work index 0 <-> 2*n0 - 10 ----
         const int nw = 2 * ta + 10;
-        for (int m = tid; m < nw; m += FM_THREADS) {
-            const float* x = demod + 2 * m + 12;        // x[-k] = demod sample feeding tap k
-            work[m] = halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
-        }
+        for (int m = tid; m < nw; m += FM_THREADS) work[m] = halfband_from(demod + 2 * m + 2);
         __syncthreads();
 
         // ---- phase 3: half-band #2 (audio_main.c:139) ----
-        for (int a = tid; a < ta; a += FM_THREADS) {
-            const float* x = work + 2 * a + 10;
-            p.audio[(int64_t) s * p.audio_stride + n0 + a] =
-                halfband_taps(x[0], x[-2], x[-4], x[-5], x[-6], x[-8], x[-10]);
-        }
+        for (int a = tid; a < ta; a += FM_THREADS)
+            p.audio[(int64_t) s * p.audio_stride + n0 + a] = halfband_from(work + 2 * a);
         // demod[] is rewritten by the next tile's phase 1 only after every thread has passed the
         // second __syncthreads above (all phase-2 reads done); work[] is rewritten in the next
         // tile's phase 2, after its first __syncthreads, which every phase-3 reader reaches first.

@@ -93,6 +93,21 @@ __device__ __forceinline__ float halfband_taps(float x0, float x2, float x4, flo
     return acc;
 }
 
+// One half-band output from an 8-byte aligned pointer to the sample feeding tap k = 10 (the
+// oldest): taps sit at +10, +8, +6, +5, +4, +2, +0 from there.  Five 64-bit loads and one 32-bit
+// load instead of seven scalar ones, and lanes that walk the array in steps of two floats read
+// contiguous words (no 2-way bank conflict).
+__device__ __forceinline__ float halfband_from(const float* oldest)
+{
+    const float2 a = *reinterpret_cast<const float2*>(oldest);          // k = 10, 9
+    const float2 b = *reinterpret_cast<const float2*>(oldest + 2);      // k = 8, 7
+    const float2 c = *reinterpret_cast<const float2*>(oldest + 4);      // k = 6, 5
+    const float2 d = *reinterpret_cast<const float2*>(oldest + 6);      // k = 4, 3
+    const float2 e = *reinterpret_cast<const float2*>(oldest + 8);      // k = 2, 1
+    const float f = oldest[10];                                         // k = 0
+    return halfband_taps(f, e.x, d.x, c.y, c.x, b.x, a.x);
+}
+
 struct FmParams {
     const uint8_t* iq;            // stream 0, first sample of the BATCH (history lies before it)
     int64_t stream_stride_bytes;
