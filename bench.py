@@ -214,7 +214,7 @@ def reference_arm(args):
     for i in range(total):
         r = run_ref_bench(n_streams, per_stream, workers)
         if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_bench could not be built or run"}))
+            emit_line({"impl": "reference", "unavailable": "oracle/_ref/ref_bench could not be built or run"})
             return 0
         if i >= total - steps:
             values.append(r["msamples_per_s"])
@@ -232,7 +232,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_line(line)
     return 0
 
 
@@ -240,8 +240,27 @@ def reference_arm(args):
 # the B200 arm
 # --------------------------------------------------------------------------------------
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun) also
+    write there, so everything else is pointed at stderr and the line goes to the saved fd."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(obj) -> None:
+    data = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -414,7 +433,7 @@ def main():
             "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
