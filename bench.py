@@ -168,28 +168,37 @@ class ClockSampler:
 # CPU reference arm (oracle/_ref): the reference's own code on the host cores
 # --------------------------------------------------------------------------------------
 
+_REF_DATA = {}       # samples_per_stream -> (path, n_unique): the synthetic captures, written once per process
+
+
+def _ref_data_file(samples_per_stream: int):
+    import atexit
+    if samples_per_stream in _REF_DATA:
+        return _REF_DATA[samples_per_stream]
+    pkg = graft.load_package()
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(shm, f"b200sdr_refbench_{os.getpid()}_{samples_per_stream}.bin")
+    n_unique = 16          # 16 distinct captures, reused round robin (timing is data-independent)
+    with open(path, "wb") as f:
+        for s in range(n_unique):
+            pkg.synth.s3_fm(samples_per_stream, seed=1000 + s).tofile(f)
+    atexit.register(lambda: os.path.exists(path) and os.unlink(path))
+    _REF_DATA[samples_per_stream] = (path, n_unique)
+    return _REF_DATA[samples_per_stream]
+
+
 def run_ref_bench(n_streams: int, samples_per_stream: int, workers: int, mode: str = "chain"):
     from oracle import pyoracle as po
     if not os.path.exists(po.REF_BENCH):
         po.build("all")
     if not os.path.exists(po.REF_BENCH):
         return None
-    pkg = graft.load_package()
-    shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
-    path = os.path.join(shm, f"b200sdr_refbench_{os.getpid()}.bin")
-    try:
-        n_unique = min(n_streams, 16)          # 16 distinct captures, reused round robin (timing is data-independent)
-        with open(path, "wb") as f:
-            for s in range(n_unique):
-                pkg.synth.s3_fm(samples_per_stream, seed=1000 + s).tofile(f)
-        res = subprocess.run([po.REF_BENCH, path, str(n_streams), str(samples_per_stream), str(workers), mode,
-                              str(n_unique)], capture_output=True, text=True, timeout=900)
-        if res.returncode != 0:
-            return None
-        return json.loads(res.stdout.strip().splitlines()[-1])
-    finally:
-        if os.path.exists(path):
-            os.unlink(path)
+    path, n_unique = _ref_data_file(samples_per_stream)
+    res = subprocess.run([po.REF_BENCH, path, str(n_streams), str(samples_per_stream), str(workers), mode,
+                          str(min(n_unique, n_streams))], capture_output=True, text=True, timeout=900)
+    if res.returncode != 0:
+        return None
+    return json.loads(res.stdout.strip().splitlines()[-1])
 
 
 def cpu_sample_shape(cpu_seconds: float, workers: int):
@@ -201,31 +210,38 @@ def cpu_sample_shape(cpu_seconds: float, workers: int):
 
 
 def reference_arm(args):
+    """The reference's own CPU implementation of the path on the host cores (oracle/_ref), all cores:
+    W untimed + exactly K timed steps, each step a bounded sample of the workload (whole streams of
+    1 s of IQ, one process per core) sized so the run ends within a couple of minutes."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     workers = os.cpu_count() or 1
-    n_streams, per_stream = cpu_sample_shape(max(2.0, args.cpu_seconds / 3), workers)
-    values, secs = [], []
-    total = args.warmup + args.steps
-    total = min(total, 8)                      # every step is seconds of CPU work; keep the run to minutes
-    steps = max(1, total - min(args.warmup, 1))
-    for i in range(total):
+    per_stream = FS
+    cal = run_ref_bench(workers, per_stream, workers)                 # calibration, untimed
+    if cal is None:
+        emit_line({"impl": "reference", "unavailable": "oracle/_ref/ref_bench could not be built or run"})
+        return 0
+    total_steps = max(1, args.steps) + max(0, args.warmup)
+    budget_s = min(10.0, max(0.5, 90.0 / total_steps))                  # CPU wall time per step
+    rounds = max(1, int(round(cal["msamples_per_s"] * 1e6 * budget_s / (per_stream * workers))))
+    n_streams = workers * rounds
+    secs = []
+    for i in range(total_steps):
         r = run_ref_bench(n_streams, per_stream, workers)
         if r is None:
-            emit_line({"impl": "reference", "unavailable": "oracle/_ref/ref_bench could not be built or run"})
+            emit_line({"impl": "reference", "unavailable": "oracle/_ref/ref_bench failed mid-run"})
             return 0
-        if i >= total - steps:
-            values.append(r["msamples_per_s"])
+        if i >= args.warmup:
             secs.append(r["seconds"])
     value = n_streams * per_stream * len(secs) / sum(secs) / 1e6
     sample = (f"{n_streams} streams x {per_stream} samples per step through the unmodified spectrum.c/rf_decimator.c/"
-              f"resample.c/audio_main.c (one process per worker); FFT inside spectrum.c is the f64 stand-in "
-              f"(FFTW3 absent); {len(secs)} timed steps of {total}")
+              f"resample.c/audio_main.c (one process per core, {workers} cores); FFT inside spectrum.c is the f64 "
+              f"stand-in (FFTW3 absent); {len(secs)} timed steps after {args.warmup} warm-up")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(secs), "warmup": total - len(secs), "ms_per_step": 1e3 * sum(secs) / len(secs),
+        "steps": len(secs), "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (FFT) / i32 / f32",
         "data": "synthetic", "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "reference", "sample": sample},
