@@ -247,3 +247,27 @@ def test_db_only_matches_all_outputs(pkg, cuda, po, synth):
         assert torch.equal(fast, both["db"])
         for s in range(min(n_streams, 2)):
             check_db(fast[s].cpu().numpy(), po.Spectrum(1024).rows(iqs[s]))
+
+
+def test_spectrogram_full_size_shift_property(pkg, cuda):
+    """BASELINE config 4 scale (a 2^27-sample capture, 65536-point Hann frames at 50 % overlap)
+    through a size-independent property: delaying the capture by one hop shifts the spectrogram
+    by exactly one row, bit for bit (frames are computed independently from the same bytes)."""
+    torch = cuda
+    n = 1 << 27
+    hop = 32768
+    g = torch.Generator(device="cuda").manual_seed(11)
+    iq = torch.randint(0, 256, (2, n, 2), dtype=torch.uint8, device="cuda", generator=g)
+    iq[1, hop:] = iq[0, :n - hop]
+    plan = pkg.SpectrumPlan(65536, hop=hop, window=pkg.WINDOW_HANN)
+    db = plan.exec(iq, db=True)["db"]
+    torch.cuda.synchronize()
+    rows = plan.rows(n)
+    assert db.shape == (2, rows, 65536) and rows == (n - 65536) // hop + 1
+    assert torch.equal(db[1, 1:], db[0, :rows - 1])
+    assert torch.isfinite(db[0]).all()
+    # white bytes: every row's mean power sits at the analytic level
+    #   E|X|^2 = sum(w^2) * E|x|^2,  E|x|^2 = 2 * (256^2 - 1) / 12 / 128^2
+    lin = torch.pow(10.0, db[0, ::64].double() / 10).mean().item()
+    want = 0.375 * 65536 * 2 * (256 ** 2 - 1) / 12 / 128 ** 2
+    assert abs(lin / want - 1) < 0.01
