@@ -143,6 +143,109 @@ __global__ void __launch_bounds__(FM_THREADS) fm_chain_kernel(const FmParams p, 
     }
 }
 
+// ---- R = 10 (the reference's default, cbb_main.c:80): one WARP per tile, no block barriers ----
+// Tile = 62 audio samples: 4*62 + 31 = 279 = 9 * 31 demodulator outputs, i.e. exactly nine
+// shuffle chunks (lane 0 of a chunk only supplies the previous phase).  Input = 2480 + 320
+// samples = 5600 bytes per TMA copy, two-deep warp-private ring; 13 KB of shared memory per
+// warp, 16 warps per SM.  Straight-line code: chunks that run past a short last tile read
+// stale bytes of the ring and their results are simply not stored.
+constexpr int F10_T = 62;
+constexpr int F10_ND = 4 * F10_T + 32;            // 280 decimated samples, local index 0 <-> 4*n0 - 32
+constexpr int F10_STAGE = F10_ND * 20;            // 5600 bytes
+constexpr int F10_NW = 2 * F10_T + 10;            // 134 first-stage outputs
+constexpr int F10_WARPS = 8;                      // per CTA: two per scheduler
+constexpr int F10_WARP_SMEM = 2 * F10_STAGE + 288 * 4 + 144 * 4 + 32;   // ring, demod[], work[], 2 mbarriers (+pad)
+static_assert(F10_WARP_SMEM % 16 == 0, "TMA destinations must stay 16-byte aligned");
+
+__global__ void __launch_bounds__(F10_WARPS * 32, 2) fm_chain10_kernel(const FmParams p, const int tiles_per_stream)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint8_t* wbase = smem + warp * F10_WARP_SMEM;
+    uint8_t* ring = wbase;
+    float* demod = reinterpret_cast<float*>(wbase + 2 * F10_STAGE);
+    float* work = demod + 288;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(work + 144);
+
+    const int64_t n_audio = p.n_samples / 40;
+    const uint32_t tps = (uint32_t) tiles_per_stream;
+    const uint32_t total_tiles = (uint32_t) p.n_streams * tps;
+    const uint32_t gw = blockIdx.x * F10_WARPS + warp;
+    const uint32_t GW = gridDim.x * F10_WARPS;
+    if (gw >= total_tiles) return;
+    const uint32_t n_mine = (total_tiles - gw + GW - 1) / GW;
+
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    auto issue = [&](uint32_t it) {
+        const uint32_t tile = gw + it * GW;
+        const uint32_t s = tile / tps;
+        const int64_t n0 = (int64_t) (tile - s * tps) * F10_T;
+        const int ta = (int) ((n_audio - n0) < F10_T ? (n_audio - n0) : F10_T);
+        const uint32_t bytes = (uint32_t) (4 * ta + 32) * 20u;
+        const uint8_t* src = p.iq + (int64_t) s * p.stream_stride_bytes + (4 * n0 - 32) * 20;
+        const int st = it & 1;
+        mbar_arrive_expect_tx(&bars[st], bytes);
+        tma_load_1d(ring + st * F10_STAGE, src, bytes, &bars[st]);
+    };
+    if (lane == 0) {
+        issue(0);
+        if (n_mine > 1) issue(1);
+    }
+
+    for (uint32_t it = 0; it < n_mine; ++it) {
+        const int st = it & 1;
+        const uint32_t tile = gw + it * GW;
+        const uint32_t s = tile / tps;
+        const int64_t n0 = (int64_t) (tile - s * tps) * F10_T;
+        const int ta = (int) ((n_audio - n0) < F10_T ? (n_audio - n0) : F10_T);
+        mbar_wait(&bars[st], (it >> 1) & 1);
+        const uint8_t* in = ring + st * F10_STAGE;
+
+        // ---- discriminator: 9 chunks of 31 outputs (resample.c:21-40, common_sp.h:40-76,
+        //      audio_main.c:110-131) ----
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            const int j = 31 * c + lane;
+            uint32_t ure, uim;
+            cic10_sum(reinterpret_cast<const uint32_t*>(in + j * 20), ure, uim);
+            const float ph = atan2_approx_dev(__uint_as_float(uim) - CIC_MAGIC, __uint_as_float(ure) - CIC_MAGIC);
+            const float prev = __shfl_up_sync(0xffffffffu, ph, 1);
+            if (lane > 0) demod[j] = fm_limit(ph, prev);
+            if (p.decimated != nullptr && j >= 32 && j < 4 * ta + 32) {
+                int2* dst = reinterpret_cast<int2*>(p.decimated) + (int64_t) s * p.dec_stride + (4 * n0 + (j - 32));
+                *dst = make_int2((int) (ure - CIC_MAGIC_BITS), (int) (uim - CIC_MAGIC_BITS));
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && it + 2 < n_mine) {
+            fence_proxy_async_smem();
+            issue(it + 2);
+        }
+        // ---- half-band #1 (audio_main.c:133); work index 0 <-> 2*n0 - 10 ----
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const int m = 32 * r + lane;
+            if (m < F10_NW) work[m] = halfband_from(demod + 2 * m + 2);
+        }
+        __syncwarp();
+        // ---- half-band #2 (audio_main.c:139) ----
+        float* out = p.audio + (int64_t) s * p.audio_stride + n0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int a = 32 * r + lane;
+            if (a < ta) out[a] = halfband_from(work + 2 * a);
+        }
+        __syncwarp();       // demod[] / work[] are rewritten by the next tile
+    }
+}
+
 // history <- last H samples of the batch (per stream); H*2 bytes, 16-byte granules
 __global__ void fm_history_carry_kernel(uint8_t* iq, int64_t stride, int n_streams, int64_t n_bytes, int hist_bytes)
 {
@@ -191,6 +294,30 @@ int launch_fm_chain(const FmParams& p, cudaStream_t stream)
         return B200_ERR_ALIGN;
     }
     if (p.n_streams == 0 || p.n_samples == 0) return B200_OK;
+    if (p.R == 10) {
+        const int64_t n_audio10 = p.n_samples / 40;
+        const int64_t tps = (n_audio10 + F10_T - 1) / F10_T;
+        const int64_t total = (int64_t) p.n_streams * tps;
+        if (total >= (1ll << 31)) {
+            set_error("fm: batch too long");
+            return B200_ERR_ARG;
+        }
+        const int smem10 = F10_WARPS * F10_WARP_SMEM;
+        static bool configured10 = false;
+        if (!configured10) {
+            B200_CUDA_TRY(cudaFuncSetAttribute(fm_chain10_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem10));
+            configured10 = true;
+        }
+        int per_sm = 0;
+        B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fm_chain10_kernel, F10_WARPS * 32, smem10));
+        if (per_sm < 1) per_sm = 1;
+        int64_t grid10 = (int64_t) sm_count() * per_sm;
+        const int64_t needed = (total + F10_WARPS - 1) / F10_WARPS;
+        if (grid10 > needed) grid10 = needed;
+        fm_chain10_kernel<<<(unsigned) grid10, F10_WARPS * 32, smem10, stream>>>(p, (int) tps);
+        B200_LAUNCH_CHECK();
+        return B200_OK;
+    }
     const int T = fm_tile_audio(p.R);
     const int64_t n_audio = p.n_samples / (4 * p.R);
     const int64_t tiles_per_stream = (n_audio + T - 1) / T;
