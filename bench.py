@@ -242,7 +242,7 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(secs), "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (FFT) / i32 / f32",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -445,7 +445,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u8 -> f32 (FFT, dB, audio); i32 (CIC)",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -103,23 +103,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
         : "memory");
 }
 
-// shared -> global bulk store (SASS: UBLKCP / UTMASTG family), tracked by bulk groups
-__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
-                 "r"(smem_u32(src_smem)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit()
-{
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read()
-{
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-
 // log2 on the MUFU unit, flush-to-zero form: no denormal pre-scaling instructions.  Inputs
 // here are sums of squares of integers (exact zero or >= 1), never denormal.  lg2(0) = -inf.
 __device__ __forceinline__ float lg2_ftz(float x)
@@ -127,12 +110,6 @@ __device__ __forceinline__ float lg2_ftz(float x)
     float r;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
-}
-
-// streaming (evict-first) 32-bit store: spectra are written once and never re-read here
-__device__ __forceinline__ void st_stream_f32(float* p, float v)
-{
-    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
 #endif  // __CUDACC__

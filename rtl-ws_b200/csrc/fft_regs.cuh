@@ -1,5 +1,5 @@
-// fft_regs.cuh -- fully unrolled in-register forward FFTs (radix-2 DIF, sizes 2..32) on
-// PACKED complex numbers: one 64-bit register pair holds (re, im) and every butterfly is a
+// fft_regs.cuh -- fully unrolled in-register forward FFTs (radix-2 DIT with FMA-fused
+// butterflies, sizes 2..64) on PACKED complex numbers: one 64-bit register pair holds (re, im) and every butterfly is a
 // Blackwell f32x2 instruction (FADD2 / FMUL2 / FFMA2, sm_100 PTX add/mul/fma.rn.f32x2).
 //
 // Why packed: the FP32 pipe retires 128 lanes/clk/SM either way (tools/ubench.cu measures
@@ -10,8 +10,9 @@
 // nothing: ptxas folds the mov.b64 shuffles below into the consuming instruction.
 //
 // One thread owns R complex points.  All twiddles inside a size-R transform are
-// compile-time constants (multiples of 2*pi/32).  Output is left in bit-reversed register
-// order; callers permute by renaming registers (bitrev<R>() is constexpr), which is free.
+// compile-time constants (multiples of 2*pi/64).  Input is taken in bit-reversed register
+// order and output is natural; callers permute by renaming registers (bitrev<R>() is
+// constexpr), which is free.
 //
 // Sign convention: X[k] = sum_j x[j] exp(-2*pi*i*j*k/R)  -- the FFTW_FORWARD transform the
 // reference plans at spectrum.c:42.
@@ -58,23 +59,6 @@ __device__ __forceinline__ c64 cfma2(c64 a, c64 b, c64 c)   // lane-wise a * b +
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
-__device__ __forceinline__ c64 cswap(c64 a)              // (im, re): an operand modifier in SASS
-{
-    float re, im;
-    cunpack(a, re, im);
-    return cpack(im, re);
-}
-
-// t * (c - i*s) = (tr*c + ti*s, ti*c - tr*s) = t * (c, c) + (ti, -tr) * (s, s).
-// Both scalars are broadcast operands (immediate or R.F32 in SASS) and (ti, -tr) is the
-// .LO_HI.NP operand modifier: two instructions, no shuffles.
-__device__ __forceinline__ c64 cmul_cs(c64 t, float c, float s)
-{
-    float tr, ti;
-    cunpack(t, tr, ti);
-    return cfma2(t, cpack(c, c), cmul2(cpack(ti, -tr), cpack(s, s)));
-}
-
 // general complex product a * w with w = (wr, wi):  (ar*wr - ai*wi, ai*wr + ar*wi)
 //   = a * (wr, wr) + (-ai, ar) * (wi, wi)
 __device__ __forceinline__ c64 cmul(c64 a, float wr, float wi)
@@ -151,18 +135,6 @@ __host__ __device__ constexpr int bitrev(int i)
         i >>= 1;
     }
     return r;
-}
-
-// t * exp(-2*pi*i*q/32), 0 <= q < 16; q is a compile-time constant after unrolling
-__device__ __forceinline__ c64 mul_w32(c64 t, int q)
-{
-    if (q == 0) return t;
-    if (q == 8) {                            // * (-i): (ti, -tr)
-        float re, im;
-        cunpack(t, re, im);
-        return cpack(im, -re);
-    }
-    return cmul_cs(t, cos32(q), sin32(q));
 }
 
 // One DIT butterfly with twiddle W = exp(-2*pi*i*q/32) on v:  (u, v) -> (u + v*W, u - v*W).
@@ -278,28 +250,6 @@ __device__ __forceinline__ void fft_dit_small(c64 (&a)[R])
         for (int g = 0; g < R; g += 2 * half) {
 #pragma unroll
             for (int k = 0; k < half; ++k) dit_butterfly(a[g + k], a[g + k + half], k * (16 / half));
-        }
-    }
-}
-
-// In-place forward DIF FFT of R points held in registers; result index bitrev<R>(p) is in a[p].
-template <int R>
-__device__ __forceinline__ void fft_dif(c64 (&a)[R])
-{
-    static_assert(R == 2 || R == 4 || R == 8 || R == 16 || R == 32, "register FFT sizes");
-#pragma unroll
-    for (int half = R / 2; half >= 1; half >>= 1) {
-#pragma unroll
-        for (int g = 0; g < R; g += 2 * half) {
-#pragma unroll
-            for (int k = 0; k < half; ++k) {
-                const int i = g + k;
-                const int j = i + half;
-                const c64 u = a[i];
-                const c64 v = a[j];
-                a[i] = cadd(u, v);
-                a[j] = mul_w32(csub(u, v), k * (16 / half));
-            }
         }
     }
 }

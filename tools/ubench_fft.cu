@@ -32,9 +32,14 @@ __global__ void __launch_bounds__(512, 1) k(const float2* twiddle, float* out, i
         } else {
             fft1024_core<true>(a, tw, xch, lane, pw);
         }
-        if (PART == 2) {            // + dB epilogue
+        if (PART >= 2) {            // + dB epilogue
 #pragma unroll
             for (int q = 0; q < 32; ++q) pw[q] = fmaf(DB_PER_LOG2, lg2_ftz(pw[q]), 1.0f);
+        }
+        if (PART == 3) {            // + 128-byte coalesced streaming stores (4 KB per frame, small L2-resident target)
+            float* dst = out + ((blockIdx.x * 16 + warp) * 4 + (it & 3)) * 1024 + lane;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) __stcs(dst + fft1024_col(q), pw[q]);
         }
 #pragma unroll
         for (int q = 0; q < 32; ++q) acc += pw[q];
@@ -52,7 +57,7 @@ void run(const char* name, const float2* d_tw, int warps)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     float* out;
     unsigned long long* cyc;
-    cudaMalloc(&out, sizeof(float) * sms * 512);
+    cudaMalloc(&out, sizeof(float) * sms * 16 * 4 * 1024 + 4096);
     cudaMalloc(&cyc, sizeof(unsigned long long) * sms);
     const int smem = warps * (2048 + FFT1024_XCH_BYTES);
     cudaFuncSetAttribute(k<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -83,6 +88,7 @@ int main()
         run<0>("load+unpack only", d_tw, warps);
         run<1>("load+fft+power", d_tw, warps);
         run<2>("load+fft+power+dB", d_tw, warps);
+        run<3>("load+fft+power+dB+STG", d_tw, warps);
     }
     return 0;
 }
