@@ -173,7 +173,10 @@ class SpectrumPlan:
             self.h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: the module globals may already be gone
+            pass
 
     def rows(self, n_samples: int) -> int:
         return int(lib().b200_spectrum_plan_rows(self.h, n_samples))
@@ -312,7 +315,10 @@ class Session:
             self.h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: the module globals may already be gone
+            pass
 
     def reset(self):
         lib().b200_session_reset(self.h)
@@ -367,7 +373,10 @@ class PushStream:
             self.h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: the module globals may already be gone
+            pass
 
 
 # --------------------------------------------------------------------------------------
