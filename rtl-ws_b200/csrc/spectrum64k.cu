@@ -4,14 +4,14 @@
 //
 // 65536 = 64 x 1024, decimation in time by 64:
 //   X[k + 1024 q] = sum_{r<64} W_64^(r q) * ( W_N^(r k) * F_r[k] ),   F_r = FFT_1024( x[64 m + r] ).
-// A CTA (8 warps, one per SM) owns one frame at a time:
+// A CTA (10 warps, one per SM) owns one frame at a time:
 //   0. the 128 KB of IQ bytes are copied into shared memory with 128-bit loads; every 128-byte
 //      row (one m, all 64 r) is word-swizzled by (m mod 32) so that the stride-128-byte reads
 //      of a polyphase branch hit 32 different banks;
-//   1. warp w runs the 32x32 register transform (fft1024_warp.cuh) on branches r = w, w+8, ...,
+//   1. warp w runs the 32x32 register transform (fft1024_warp.cuh) on branches r = w, w+10, ...,
 //      multiplies by W_N^(r k) (table stored [r][k], read coalesced) and writes Z[r][k] to this
 //      CTA's 512 KB slice of a global scratch that stays in the 126 MB L2;
-//   2. block barrier; thread t takes k = t, t+256, t+512, t+768: 64 coalesced loads of Z[.][k],
+//   2. block barrier; thread t takes k = t, t+320, ... (< 1024): 64 coalesced loads of Z[.][k],
 //      a 64-point FFT in registers, |X|^2, K-frame accumulation with the cumulative
 //      DC-position patch (spectrum.c:30-33), dB / power / u8, coalesced stores.
 // Arithmetic per frame as in spectrum1024.cu (spectrum.c:15-58, cbb_main.c:112-128); the window
@@ -25,8 +25,8 @@ namespace b200 {
 namespace {
 
 constexpr int N64K = 65536;
-constexpr int S64_THREADS = 256;
-constexpr int S64_WARPS = 8;
+constexpr int S64_THREADS = 320;
+constexpr int S64_WARPS = 10;                                             // 128 KB frame + 10 exchange tiles = 218 KB
 constexpr int S64_FRAME_BYTES = 2 * N64K;                                  // 131072
 constexpr int S64_SMEM = S64_FRAME_BYTES + S64_WARPS * FFT1024_XCH_BYTES + 16;
 
@@ -47,9 +47,6 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
     const int64_t total = (int64_t) p.n_streams * p.n_rows;
     const int K = MULTI ? p.K : 1;
     const float dboff = p.db_offset - 16.0f * DB_PER_LOG2;
-
-    float2 tw[32];
-    fft1024_load_twiddles(p.twiddle, lane, tw);
 
     auto emit = [&](size_t row_base, int bin, float pw) {
         const int col = (bin + N64K / 2) & (N64K - 1);
@@ -87,7 +84,10 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
             }
             __syncthreads();
 
-            // ---- 1. polyphase branches r = warp, warp + 8, ... ----
+            // ---- 1. polyphase branches r = warp, warp + 10, ...  (the lane-private inter-pass twiddles
+            //         are re-read per frame so that they are not live during phase 2) ----
+            float2 tw[32];
+            fft1024_load_twiddles(p.twiddle, lane, tw);
             for (int r = warp; r < 64; r += S64_WARPS) {
                 c64 a[32];
                 {
@@ -123,9 +123,10 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
             }
             __syncthreads();          // Z[.][.] of this frame is complete and visible to the CTA
 
-            // ---- 2. 64-point transforms across r for k = tid + 256 g ----
-            for (int g = 0; g < 4; ++g) {
-                const int k = tid + 256 * g;
+            // ---- 2. 64-point transforms across r for k = tid + 320 g ----
+            for (int g = 0; g < (1024 + S64_THREADS - 1) / S64_THREADS; ++g) {
+                const int k = tid + S64_THREADS * g;
+                if (k >= 1024) break;
                 c64 z[64];
 #pragma unroll
                 for (int r = 0; r < 64; ++r) z[bitrev<64>(r)] = Z[r * 1024 + k];
@@ -141,10 +142,10 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
                     } else if (bin != 0) {
                         emit(row_base, bin, pw);
                     }
-                    if (g == 3 && q == 63) dcacc = fmaf((float) (K - j), pw, dcacc);     // bin N-1 lives in thread 255
+                    if (k == 1023 && q == 63) dcacc = fmaf((float) (K - j), pw, dcacc);  // bin N-1
                 }
             }
-            if (j == K - 1 && tid == S64_THREADS - 1) *dc_slot = dcacc;
+            if (j == K - 1 && tid == 1023 % S64_THREADS) *dc_slot = dcacc;
             __syncthreads();          // frame32 / Z are rewritten by the next frame; dc_slot is visible
         }
 
