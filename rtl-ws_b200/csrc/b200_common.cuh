@@ -26,6 +26,12 @@ int sm_count();
         }                                                                                \
     } while (0)
 
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per (kernel, device): the
+// attribute belongs to the device's copy of the function, and a process may drive several GPUs.
+int ensure_dynamic_smem(const void* kernel, int bytes);
+// Resident CTAs per SM for (kernel, block, smem), cached per device like the attribute.
+int cached_occupancy(const void* kernel, int block_threads, int smem_bytes);
+
 #define B200_LAUNCH_CHECK()                                                              \
     do {                                                                                 \
         ::b200::g_launches.fetch_add(1, std::memory_order_relaxed);                      \

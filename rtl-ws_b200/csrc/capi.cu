@@ -4,7 +4,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "b200_common.cuh"
@@ -38,6 +40,39 @@ int sm_count()
         cached_dev = dev;
     }
     return cached;
+}
+
+namespace {
+std::mutex g_attr_mutex;
+std::map<std::pair<const void*, int>, int> g_smem_set;          // (kernel, device) -> bytes granted
+std::map<std::tuple<const void*, int, int, int>, int> g_occ;     // (kernel, device, block, smem) -> CTAs / SM
+}  // namespace
+
+int ensure_dynamic_smem(const void* kernel, int bytes)
+{
+    int dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    auto key = std::make_pair(kernel, dev);
+    auto it = g_smem_set.find(key);
+    if (it != g_smem_set.end() && it->second >= bytes) return B200_OK;
+    B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    g_smem_set[key] = bytes;
+    return B200_OK;
+}
+
+int cached_occupancy(const void* kernel, int block_threads, int smem_bytes)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    auto key = std::make_tuple(kernel, dev, block_threads, smem_bytes);
+    auto it = g_occ.find(key);
+    if (it != g_occ.end()) return it->second;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, block_threads, smem_bytes) != cudaSuccess || n < 1) n = 1;
+    g_occ[key] = n;
+    return n;
 }
 
 // launchers implemented next to their kernels

@@ -218,14 +218,8 @@ int launch_chain_fused(const uint8_t* d_iq, int64_t stride, int n_streams, int64
     // the plan's offset is 10*log10(g / (K * 2^14)) with K = 1; the fused unpack carries 2^30
     p.dboff = db_offset - 16.0f * DB_PER_LOG2;
     p.twiddle = twiddle;
-    static bool configured = false;
-    if (!configured) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(chain_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM));
-        configured = true;
-    }
-    int ctas_per_sm = 0;
-    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, chain_fused_kernel, CF_THREADS, CF_SMEM));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (int rc = ensure_dynamic_smem((const void*) chain_fused_kernel, CF_SMEM)) return rc;
+    const int ctas_per_sm = cached_occupancy((const void*) chain_fused_kernel, CF_THREADS, CF_SMEM);
     int64_t grid = (int64_t) sm_count() * ctas_per_sm;
     const int64_t needed = (total + CF_GROUPS - 1) / CF_GROUPS;
     if (grid > needed) grid = needed;

@@ -303,14 +303,8 @@ int launch_fm_chain(const FmParams& p, cudaStream_t stream)
             return B200_ERR_ARG;
         }
         const int smem10 = F10_WARPS * F10_WARP_SMEM;
-        static bool configured10 = false;
-        if (!configured10) {
-            B200_CUDA_TRY(cudaFuncSetAttribute(fm_chain10_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem10));
-            configured10 = true;
-        }
-        int per_sm = 0;
-        B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fm_chain10_kernel, F10_WARPS * 32, smem10));
-        if (per_sm < 1) per_sm = 1;
+        if (int rc = ensure_dynamic_smem((const void*) fm_chain10_kernel, smem10)) return rc;
+        const int per_sm = cached_occupancy((const void*) fm_chain10_kernel, F10_WARPS * 32, smem10);
         int64_t grid10 = (int64_t) sm_count() * per_sm;
         const int64_t needed = (total + F10_WARPS - 1) / F10_WARPS;
         if (grid10 > needed) grid10 = needed;
@@ -327,15 +321,9 @@ int launch_fm_chain(const FmParams& p, cudaStream_t stream)
     }
     const int stage_bytes = (4 * T + 32) * 2 * p.R;
     const int smem = 2 * stage_bytes + (4 * T + 32) * 4 + (2 * T + 16) * 4 + 16;
-    auto kern = (p.R == 10) ? fm_chain_kernel<10> : fm_chain_kernel<0>;
-    static bool configured[2] = {false, false};
-    if (!configured[p.R == 10]) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32768 + 8192));
-        configured[p.R == 10] = true;
-    }
-    int ctas_per_sm = 0;
-    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, FM_THREADS, smem));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    auto kern = fm_chain_kernel<0>;
+    if (int rc = ensure_dynamic_smem((const void*) kern, 2 * 32768 + 8192)) return rc;
+    const int ctas_per_sm = cached_occupancy((const void*) kern, FM_THREADS, smem);
     int64_t grid = (int64_t) sm_count() * ctas_per_sm;
     const int64_t total_tiles = (int64_t) p.n_streams * tiles_per_stream;
     if (grid > total_tiles) grid = total_tiles;

@@ -209,15 +209,8 @@ int launch_spectrum1024(const SpecParams& p, cudaStream_t stream)
     const bool window = p.window != nullptr;
     auto kern = multi ? (window ? spectrum1024_kernel<true, true> : spectrum1024_kernel<true, false>)
                       : (window ? spectrum1024_kernel<false, true> : spectrum1024_kernel<false, false>);
-    static bool configured[4] = {false, false, false, false};
-    const int which = (multi ? 2 : 0) + (window ? 1 : 0);
-    if (!configured[which]) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM));
-        configured[which] = true;
-    }
-    int ctas_per_sm = 0;
-    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, WARPS_PER_CTA * 32, CTA_SMEM));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (int rc = ensure_dynamic_smem((const void*) kern, CTA_SMEM)) return rc;
+    const int ctas_per_sm = cached_occupancy((const void*) kern, WARPS_PER_CTA * 32, CTA_SMEM);
     // persistent grid: a whole number of CTAs per SM, never more warps than rows
     uint64_t grid = (uint64_t) sm_count() * (uint64_t) ctas_per_sm;
     const uint64_t needed = (total + WARPS_PER_CTA - 1) / WARPS_PER_CTA;

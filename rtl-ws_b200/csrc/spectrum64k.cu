@@ -168,7 +168,7 @@ int launch_spectrum64k(const SpecParams& p, const Spec64kExtra& x, cudaStream_t 
     if (total == 0) return B200_OK;
     auto kern = p.K > 1 ? (p.window ? spectrum64k_kernel<true, true> : spectrum64k_kernel<false, true>)
                         : (p.window ? spectrum64k_kernel<true, false> : spectrum64k_kernel<false, false>);
-    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S64_SMEM));
+    if (int rc = ensure_dynamic_smem((const void*) kern, S64_SMEM)) return rc;
     int64_t grid = x.scratch_ctas;
     if (grid > total) grid = total;
     kern<<<(unsigned) grid, S64_THREADS, S64_SMEM, stream>>>(p, x);

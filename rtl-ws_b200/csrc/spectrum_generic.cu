@@ -205,7 +205,7 @@ int launch_spectrum_generic(const SpecParams& p, int N, int kind, cudaStream_t s
     auto kern = kind == IN_CU8 ? spectrum_generic_kernel<IN_CU8>
                                : (kind == IN_CS32 ? spectrum_generic_kernel<IN_CS32> : spectrum_generic_kernel<IN_RF32>);
     if (smem > 48 * 1024)
-        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (int rc = ensure_dynamic_smem((const void*) kern, smem)) return rc;
     kern<<<grid, GEN_THREADS, smem, stream>>>(p, N, sample_bytes, scratch, acc_scratch);
     B200_LAUNCH_CHECK();
     return B200_OK;

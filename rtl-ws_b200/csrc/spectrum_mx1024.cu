@@ -206,10 +206,8 @@ int launch_m(const SpecParams& p, cudaStream_t stream)
     }
     auto kern = p.K > 1 ? (p.window ? spectrum_mx1024_kernel<M, true, true> : spectrum_mx1024_kernel<M, false, true>)
                         : (p.window ? spectrum_mx1024_kernel<M, true, false> : spectrum_mx1024_kernel<M, false, false>);
-    B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    int ctas_per_sm = 0;
-    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, C::THREADS, C::SMEM));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (int rc = ensure_dynamic_smem((const void*) kern, C::SMEM)) return rc;
+    const int ctas_per_sm = cached_occupancy((const void*) kern, C::THREADS, C::SMEM);
     uint64_t grid = (uint64_t) sm_count() * (uint64_t) ctas_per_sm;
     if (grid > total) grid = total;
     kern<<<(unsigned) grid, C::THREADS, C::SMEM, stream>>>(p);
