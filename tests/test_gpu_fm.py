@@ -168,3 +168,46 @@ def test_chain_full_size_properties(pkg, cuda):
     assert torch.equal(db1[0], db[37]) and torch.equal(audio1[0], audio[37])
     # |audio| <= (sum |h|)^2 of the two half-bands on a +-1 limited input
     assert audio.abs().max().item() <= 1.46404 ** 2 + 1e-6
+
+
+@pytest.mark.parametrize("n_streams,n_tiles", [(1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (2, 7), (3, 13), (1, 31), (5, 1)])
+def test_chain_pipeline_edges(pkg, cuda, po, synth, n_streams, n_tiles):
+    """Few tiles per CTA / per group: ring prologue shorter than its depth, groups with no work,
+    the last tile's audio job after the loop, history at the very start of every stream."""
+    torch = cuda
+    n = 5120 * n_tiles
+    iqs = np.stack([synth.s1_noise(n, seed=400 + s) if s % 2 else synth.s3_fm(n, seed=400 + s)
+                    for s in range(n_streams)])
+    ring = pkg.StreamRing(n_streams, n)
+    ring.load(iqs)
+    db, audio = pkg.chain_exec(ring)
+    audio_only, dec = pkg.fm_exec(ring, decimated=True)
+    torch.cuda.synchronize()
+    db, audio, audio_only, dec = db.cpu().numpy(), audio.cpu().numpy(), audio_only.cpu().numpy(), dec.cpu().numpy()
+    for s in range(n_streams):
+        want_dec, want_audio = oracle_stream(po, iqs[s])
+        assert np.array_equal(dec[s], want_dec)
+        assert np.abs(audio[s] - want_audio).max() <= AUDIO_TOL
+        assert np.abs(audio_only[s] - want_audio).max() <= AUDIO_TOL
+        rows = po.Spectrum(1024).rows(iqs[s])
+        ok = rows > 1e-6 * rows.mean(axis=1, keepdims=True)
+        assert np.abs(db[s][ok] - 10 * np.log10(rows[ok])).max() <= 0.01
+
+
+def test_fm_tile_boundaries_r10(pkg, cuda, po, synth):
+    """Audio lengths around the 62-sample tile of the R = 10 kernel (n_samples only has to be a
+    multiple of 40): whole tiles, one short tile, a single audio sample."""
+    torch = cuda
+    for n_audio in (1, 2, 61, 62, 63, 124, 125, 1000):
+        n = 40 * n_audio
+        if n % 8:
+            n_audio += 1          # n_samples must also be a multiple of 8
+            n = 40 * n_audio
+        iq = synth.s3_fm(n, seed=n_audio)
+        ring = pkg.StreamRing(1, n)
+        ring.load(iq[None])
+        audio, dec = pkg.fm_exec(ring, decimated=True)
+        torch.cuda.synchronize()
+        want_dec, want_audio = oracle_stream(po, iq)
+        assert np.array_equal(dec.cpu().numpy()[0], want_dec)
+        assert np.abs(audio.cpu().numpy()[0] - want_audio).max() <= AUDIO_TOL
