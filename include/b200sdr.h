@@ -174,6 +174,57 @@ int b200_stream_poll(b200_stream* s);           /* deliver whatever has finished
 int b200_stream_flush(b200_stream* s);          /* wait for and deliver every submitted batch */
 int64_t b200_stream_pending_samples(const b200_stream* s, int stream);   /* buffered, not yet a whole batch */
 
+/* ---- websocket wire formats: what the reference's main.c puts on the socket ----------------
+ *
+ * Replaces the formatting in the LWS_CALLBACK_SERVER_WRITEABLE branch of main.c (a GPU box
+ * serving many UI sessions wants what comes back over PCIe to be ready for lws_write):
+ *   main.c:80-84   spectrum message  "t s;f %u;b %u;s %d;d" + the payload bytes of
+ *                  cbb_get_spectrum_payload (cbb_main.c:106-135), one binary message;
+ *   main.c:86-110  audio message  "FF;t a;d" + 8 writes of 2048 bytes of float32 audio
+ *                  (first opens a binary message, the rest are continuations, all but the
+ *                  last carry NO_FIN): 8 + 16384 bytes once the socket has joined them.
+ * Parsed by rtl_ui.js:98-141.  main.c formats the header into a 30-byte stack buffer
+ * (main.c:46) and overruns it for 8- and 9-digit frequencies; these functions do not.
+ */
+#define B200_WIRE_SPECTRUM_HEADER_MAX 48      /* >= the widest "t s;f %u;b %u;s %d;d" (45) */
+#define B200_WIRE_AUDIO_FRAGMENTS 8           /* main.c:99-110 */
+#define B200_WIRE_AUDIO_FRAGMENT_BYTES 2048   /* main.c:99 */
+#define B200_WIRE_AUDIO_MESSAGE_BYTES (8 + B200_WIRE_AUDIO_FRAGMENTS * B200_WIRE_AUDIO_FRAGMENT_BYTES)
+/* write flags of a fragment (INTEGRATION.md maps them to LWS_WRITE_BINARY / _CONTINUATION / _NO_FIN) */
+#define B200_WIRE_BINARY 1
+#define B200_WIRE_CONTINUATION 2
+#define B200_WIRE_NO_FIN 0x40
+/* audio_get_audio_payload (audio_main.c:40-72) re-sends the first 512 samples of a finished
+ * pool buffer in place of the first 512 of the next one.  Off by default; with this flag the
+ * emitted sample order is the reference's, byte for byte. */
+#define B200_WIRE_REFERENCE_DRAIN 1
+
+/* Header only; returns its length (no terminating NUL is written), B200_ERR_ARG if it does not fit. */
+int b200_wire_spectrum_header(char* dst, int dst_len, uint32_t freq_hz, uint32_t sample_rate_hz, int gain_db);
+/* Host assembly of one message from host payload bytes; returns the message length. */
+int b200_wire_spectrum_message(uint8_t* dst, int dst_len, uint32_t freq_hz, uint32_t sample_rate_hz, int gain_db,
+                               const uint8_t* payload, int n_bins);
+/* Batched, on the device: message s = header(freq_hz[s], sample_rate_hz[s], gain_db[s]) + the n_bins
+ * payload bytes at d_payload + s * payload_stride (what b200_spectrum_exec wrote to d_db_u8 or
+ * b200_chain_exec to d_avg_u8), written to d_msgs + s * msg_stride (>= HEADER_MAX + n_bins, bytes
+ * past the message up to the next multiple of 4 are zeroed).  freq_hz / sample_rate_hz / gain_db /
+ * lens are host arrays; lens[s] (nullable) receives the length.  Strides and pointers: multiples of 4. */
+int b200_wire_spectrum_messages(const uint8_t* d_payload, int64_t payload_stride, int n_streams, int n_bins,
+                                const uint32_t* freq_hz, const uint32_t* sample_rate_hz, const int32_t* gain_db,
+                                uint8_t* d_msgs, int64_t msg_stride, int32_t* lens, void* cuda_stream);
+/* Batched audio messages on the device.  Message m of stream s holds wire samples
+ * first_wire_sample + 4096 m .. + 4095 of d_audio + s * audio_stride (floats), at
+ * d_msgs + s * msg_stride + m * B200_WIRE_AUDIO_MESSAGE_BYTES.  flags = 0: wire sample w is audio
+ * sample w.  B200_WIRE_REFERENCE_DRAIN: wire sample w is audio sample
+ * b200_wire_reference_drain_index(w, buffer_len) (buffer_len = 5120, audio_main.c:90,100).
+ * d_audio must start at the stream's first audio sample in that mode. */
+int b200_wire_audio_messages(const float* d_audio, int64_t audio_stride, int n_streams, int64_t first_wire_sample,
+                             int n_messages, int flags, int buffer_len, uint8_t* d_msgs, int64_t msg_stride,
+                             void* cuda_stream);
+/* The lws_write calls of one audio message: fragment `index` (0..7) is `len` bytes at `offset` with `flags`. */
+int b200_wire_audio_fragment(int index, int32_t* offset, int32_t* len, int32_t* flags);
+int64_t b200_wire_reference_drain_index(int64_t wire_sample, int buffer_len);
+
 void* b200_host_alloc(uint64_t bytes);          /* pinned host memory */
 void b200_host_free(void* p);
 

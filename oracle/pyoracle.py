@@ -312,6 +312,12 @@ class Ref:
         lib.ref_fm_copy_demod.argtypes = [_f32p, C.c_int]
         lib.ref_cbb_run.argtypes = [_u8p, C.c_int64, C.c_int, _u8p, _f64p, _i32p, C.c_int,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        lib.ref_ws_set_log.argtypes = [_u8p, C.c_int64, _i32p, C.c_int]
+        lib.ref_ws_n_bytes.restype = C.c_int64
+        lib.ref_ws_command.argtypes = [C.c_char_p]
+        lib.ref_ws_queue_command.argtypes = [C.c_char_p]
+        lib.ref_ws_pump.argtypes = [C.c_int]
+        lib.ref_ws_attach.argtypes = [C.c_int]
         lib.rf_decimator_alloc.restype = C.c_void_p
         lib.rf_decimator_set_parameters.argtypes = [C.c_void_p, C.c_double, C.c_int]
         lib.rf_decimator_decimate_cmplx_u8.argtypes = [C.c_void_p, _u8p, C.c_int]
@@ -410,6 +416,37 @@ class Ref:
         nd, na = self.lib.ref_fm_n_decimated(), self.lib.ref_fm_n_audio()
         return dict(payload=payload[:k].copy(), power=power[:k].copy(), count=count[:k].copy(),
                     decimated=dec[:nd].copy(), audio=audio[:na].copy())
+
+
+    # main.c's websocket callback on top of the whole driver -------------------------------
+    def ws_run(self, iq: np.ndarray, commands=("start",), max_bytes: int | None = None):
+        """Replay `iq` through the unmodified driver with the unmodified main.c callback as the
+        consumer (pumped after every USB buffer).  The client connects at the first poll and sends
+        `commands` as text messages (main.c:139-176).  -> list of (write_mode, bytes) in
+        the order main.c handed them to lws_write."""
+        iq = np.ascontiguousarray(iq, dtype=np.uint8).reshape(-1)
+        n = len(iq) // 2
+        cap = max_bytes if max_bytes is not None else n // 40 * 4 * 2 + (n // 100000 + 16) * 2048 + (1 << 16)
+        log = np.zeros(cap, dtype=np.uint8)
+        max_rec = cap // 512 + 64
+        rec = np.zeros((max_rec, 3), dtype=np.int32)
+        self.lib.ref_ws_set_log(log, cap, rec.reshape(-1), max_rec)
+        self.lib.ref_ws_attach(1)
+        for c in commands:
+            if self.lib.ref_ws_queue_command(c.encode()):
+                raise ValueError(f"cannot queue command {c!r}")
+        dummy_u8 = np.zeros(1024, dtype=np.uint8)
+        dummy_f64 = np.zeros(1024, dtype=np.float64)
+        dummy_i32 = np.zeros(1, dtype=np.int32)
+        self.lib.ref_cbb_run(iq, len(iq), 0, dummy_u8, dummy_f64, dummy_i32, 0, None, 0, None, 0)
+        self.lib.ref_ws_attach(0)
+        if self.lib.ref_ws_overflowed():
+            raise RuntimeError("ws log overflow")
+        k = self.lib.ref_ws_n_records()
+        out = []
+        for off, ln, mode in rec[:k]:
+            out.append((int(mode), log[off:off + ln].tobytes()))
+        return out
 
 
 class DropIn(Ref):

@@ -53,6 +53,10 @@ static int* g_count_out = NULL;           /* [max_spectra] */
 static int g_max_spectra = 0;
 static int g_n_spectra = 0;
 static int g_gain_db = 0;
+/* optional replacement for the consumer poll (ref_harness_ws.c drives main.c's callback from it);
+ * with a hook set the audio stays in audio_main.c's pool for the hook to fetch */
+static void (*g_consumer_hook)(void) = NULL;
+void ref_cbb_set_consumer(void (*hook)(void)) { g_consumer_hook = hook; }
 
 int rtl_init(struct rtl_dev** dev, int dev_index)
 {
@@ -74,6 +78,11 @@ void rtl_close(struct rtl_dev* dev) { free(dev); }
 
 static void poll_consumer(void)
 {
+    if (g_consumer_hook != NULL)
+    {
+        g_consumer_hook();
+        return;
+    }
     /* main.c:77-84: if a new spectrum is there, fetch the payload */
     if (cbb_new_spectrum_available() && g_n_spectra < g_max_spectra)
     {
@@ -153,7 +162,8 @@ int ref_cbb_run(const uint8_t* capture, int64_t capture_bytes, int gain_db,
     cbb_init(192000);                                    /* main.c:199, DECIMATED_TARGET_BW_HZ main.c:23 */
     rf_decimator_add_callback(cbb_rf_decimator(), ref_cbb_capture_dec);
     rf_decimator_add_callback(cbb_rf_decimator(), audio_fm_demodulator);   /* main.c:205 */
-    rf_decimator_add_callback(cbb_rf_decimator(), ref_cbb_drain_audio);
+    if (g_consumer_hook == NULL)
+        rf_decimator_add_callback(cbb_rf_decimator(), ref_cbb_drain_audio);
 
     pthread_mutex_lock(&g_go_mutex);
     g_go = 1;

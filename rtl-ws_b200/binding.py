@@ -30,6 +30,8 @@ EXPORTED_SYMBOLS = [
     "b200_session_create", "b200_session_destroy", "b200_session_reset", "b200_session_chain",
     "b200_stream_create", "b200_stream_destroy", "b200_stream_set_sinks", "b200_stream_push", "b200_stream_poll",
     "b200_stream_flush", "b200_stream_pending_samples",
+    "b200_wire_spectrum_header", "b200_wire_spectrum_message", "b200_wire_spectrum_messages",
+    "b200_wire_audio_messages", "b200_wire_audio_fragment", "b200_wire_reference_drain_index",
     "b200_host_alloc", "b200_host_free",
     "spectrum_alloc", "spectrum_add_cmplx_u8", "spectrum_add_cmplx_s32", "spectrum_add_real_f32", "spectrum_free",
     "cic_decimate", "halfband_decimate",
@@ -99,6 +101,13 @@ def lib() -> C.CDLL:
     L.b200_stream_flush.argtypes = [vp]
     L.b200_stream_pending_samples.restype = i64
     L.b200_stream_pending_samples.argtypes = [vp, i32]
+    L.b200_wire_spectrum_header.argtypes = [C.c_char_p, i32, C.c_uint32, C.c_uint32, i32]
+    L.b200_wire_spectrum_message.argtypes = [vp, i32, C.c_uint32, C.c_uint32, i32, vp, i32]
+    L.b200_wire_spectrum_messages.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, i64, vp, vp]
+    L.b200_wire_audio_messages.argtypes = [vp, i64, i32, i64, i32, i32, i32, vp, i64, vp]
+    L.b200_wire_audio_fragment.argtypes = [i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.b200_wire_reference_drain_index.restype = i64
+    L.b200_wire_reference_drain_index.argtypes = [i64, i32]
     L.b200_host_alloc.restype = vp
     L.b200_host_alloc.argtypes = [u64]
     L.b200_host_free.argtypes = [vp]

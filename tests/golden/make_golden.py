@@ -125,6 +125,17 @@ def main() -> None:
         save(f"cbb_gain{gain}.npz", iq_sha=sha(iq), seed=7, n=len(iq), payload=out["payload"], power=out["power"],
              count=out["count"], audio_sha=sha(out["audio"]), audio_head=out["audio"][:2048])
 
+    # ---- the websocket callback of the unmodified main.c on top of the driver (main.c:74-111) ----
+    iq = synth.s3_fm(131072 * 7, seed=79)
+    freq, rate, gain = 99_900_000, 2_048_000, 17
+    records = po.Ref().ws_run(iq, commands=(f"spectrumgain {gain}", f"freq {freq // 1000}", "start"))
+    drv = po.Ref().cbb_run(iq, gain_db=gain)
+    blob = np.frombuffer(b"".join(b for _, b in records), dtype=np.uint8)
+    offs = np.cumsum([0] + [len(b) for _, b in records[:-1]])
+    rec = np.array([[o, len(b), m] for o, (m, b) in zip(offs, records)], dtype=np.int64)
+    save("ws_stream.npz", iq_sha=sha(iq), seed=79, n=len(iq), freq=freq, rate=rate, gain=gain, records=rec, bytes=blob,
+         payload=drv["payload"], audio=drv["audio"])
+
 
 if __name__ == "__main__":
     main()

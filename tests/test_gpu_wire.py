@@ -1,0 +1,146 @@
+"""Wire formats on the GPU: the batched device-side emitters against
+the host assembly, the product path (chain kernels -> wire kernels) against the byte stream the
+unmodified main.c produced (tests/golden/ws_stream.npz), and main.c itself running on top of
+libb200sdr.so (the drop-in build) against main.c on top of the reference DSP."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as _po
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ws_stream.npz")
+
+
+@pytest.fixture(scope="module")
+def wire(pkg):
+    return pkg.wire
+
+
+@pytest.mark.parametrize("n_bins", [16, 1024, 4096])
+def test_spectrum_messages_equal_host_assembly(pkg, cuda, wire, n_bins):
+    torch = cuda
+    rng = np.random.default_rng(n_bins)
+    # header lengths 25..45 bytes: every alignment of the payload inside a 4-byte word
+    tunings = [(0, 0, 0), (7, 1, -1), (100000000, 2048000, 0), (99900000, 2048000, 17), (4294967295, 4294967295, -2147483648),
+               (88000000, 250000, 5), (433920000, 1024000, -12), (1, 22, 333), (12345, 678, 9), (999999999, 99, 100)]
+    n = len(tunings)
+    payload = rng.integers(0, 256, size=(n, n_bins), dtype=np.uint8)
+    d_payload = torch.as_tensor(payload).cuda()
+    before = pkg.launch_count()
+    msgs, lens = wire.spectrum_messages(d_payload, [t[0] for t in tunings], [t[1] for t in tunings], [t[2] for t in tunings])
+    torch.cuda.synchronize()
+    assert pkg.launch_count() == before + 1
+    msgs = msgs.cpu().numpy()
+    seen = set()
+    for s, (f, r, g) in enumerate(tunings):
+        want = wire.spectrum_message(f, r, g, payload[s])
+        assert lens[s] == len(want)
+        assert msgs[s, :lens[s]].tobytes() == want
+        pad = (-lens[s]) % 4
+        assert (msgs[s, lens[s]:lens[s] + pad] == 0).all()
+        seen.add((len(want) - n_bins) % 4)
+    assert seen == {0, 1, 2, 3}
+
+
+def test_spectrum_messages_argument_errors(pkg, cuda, wire):
+    torch = cuda
+    d = torch.zeros((2, 1022), dtype=torch.uint8, device="cuda")
+    with pytest.raises(pkg.B200Error, match="multiple of 4"):
+        wire.spectrum_messages(d, 1, 2, 3)
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_audio_messages_equal_numpy(pkg, cuda, wire, flags):
+    torch = cuda
+    rng = np.random.default_rng(5 + flags)
+    n_streams, n_msgs, first = 3, 7, 2 * 4096
+    audio = rng.standard_normal((n_streams, first + n_msgs * 4096 + 64)).astype(np.float32)
+    d_audio = torch.as_tensor(audio).cuda()
+    msgs = wire.audio_messages(d_audio, first, n_msgs, flags=flags).cpu().numpy()
+    assert msgs.shape == (n_streams, n_msgs, wire.AUDIO_MESSAGE_BYTES)
+    w = first + np.arange(n_msgs * 4096)
+    src = np.array([wire.reference_drain_index(int(j)) for j in w]) if flags else w
+    for s in range(n_streams):
+        assert (msgs[s, :, :8] == np.frombuffer(b"FF;t a;d", dtype=np.uint8)).all()
+        body = np.ascontiguousarray(msgs[s, :, 8:]).view("<f4").reshape(-1)
+        assert np.array_equal(body, audio[s][src])
+    if flags:
+        assert (src != w).sum() == 512 * ((first + n_msgs * 4096 - 1) // 5120 - (first - 1) // 5120)
+
+
+def test_product_path_against_golden_ws_stream(pkg, cuda, po, synth, wire):
+    """IQ -> GPU kernels -> GPU wire emitters, compared with what main.c put on the socket."""
+    torch = cuda
+    g = np.load(GOLDEN)
+    iq = synth.s3_fm(int(g["n"]), seed=int(g["seed"]))
+    assert hashlib.sha256(iq.tobytes()).hexdigest() == str(g["iq_sha"])
+    freq, rate, gain = int(g["freq"]), int(g["rate"]), int(g["gain"])
+    records = [(int(m), g["bytes"][o:o + n].tobytes()) for o, n, m in g["records"]]
+    spec = [b for m, b in records if b.startswith(b"t s;")]
+    frags = [b for m, b in records if not b.startswith(b"t s;")]
+
+    # FM branch: whole 204800-sample blocks, as rf_decimator delivers them (rf_decimator.c:65-66)
+    n = (len(iq) // 204800) * 204800
+    ring = pkg.StreamRing(1, n)
+    ring.load(iq[:n])
+    audio, _ = pkg.fm_exec(ring)
+    n_msgs = len(frags) // 8
+    msgs = wire.audio_messages(audio, 0, n_msgs, flags=wire.REFERENCE_DRAIN).cpu().numpy()[0]
+    table = wire.audio_fragments()
+    for i, want in enumerate(frags[:8 * n_msgs]):
+        off, ln, _ = table[i % 8]
+        got = msgs[i // 8, off:off + ln].tobytes()
+        skip = 8 if i % 8 == 0 else 0
+        assert got[:skip] == want[:skip] and len(got) == len(want)
+        a = np.frombuffer(got[skip:], dtype="<f4")
+        b = np.frombuffer(want[skip:], dtype="<f4")
+        assert np.abs(a - b).max() <= 1e-4, f"fragment {i}"
+
+    # spectrum branch: 6-frame average at the start of every 131072-sample source buffer
+    # (cbb_main.c:40-70); the driver publishes one every >= 250 ms, i.e. every 4th buffer here
+    plan = pkg.SpectrumPlan(1024, K=6, row_hop=131072, gain_db=gain)
+    d_iq = torch.as_tensor(iq).cuda().reshape(1, -1, 2)
+    out = plan.exec(d_iq, db=True, db_u8=True)
+    rows_u8 = out["db_u8"][0]
+    m, lens = wire.spectrum_messages(rows_u8, freq, rate, gain)
+    m = m.cpu().numpy()
+    dbf = out["db"][0].cpu().numpy()
+    row = -1
+    for want in spec:
+        best = None
+        for r in range(row + 1, rows_u8.shape[0]):
+            got = m[r, :lens[r]].tobytes()
+            if len(got) == len(want) and got[:lens[r] - 1024] == want[:lens[r] - 1024]:
+                d = np.frombuffer(got[-1024:], dtype=np.uint8) != np.frombuffer(want[-1024:], dtype=np.uint8)
+                if d.mean() < 0.01 and (np.abs(dbf[r][d] - np.rint(dbf[r][d])) <= 0.01).all():
+                    best = r
+                    break
+        assert best is not None, "no GPU spectrum message matches the one main.c sent"
+        row = best
+
+
+@pytest.mark.skipif(not _po.have_dropin(), reason="oracle/_ref/libdropin_rtlws.so not built")
+def test_unmodified_main_c_over_the_gpu_library(pkg, cuda, po, synth):
+    """main.c + cbb_main.c + audio_main.c, unmodified, linked against libb200sdr.so: the socket sees the
+    same messages as with the reference DSP underneath."""
+    iq = synth.s3_fm(131072 * 7, seed=81)
+    cmds = ("spectrumgain 17", "freq 99900", "start")
+    want = po.Ref().ws_run(iq, commands=cmds)
+    before = pkg.launch_count()
+    got = po.DropIn().ws_run(iq, commands=cmds)
+    assert pkg.launch_count() > before
+    assert [(m, len(b)) for m, b in got] == [(m, len(b)) for m, b in want]
+    for (m, a), (_, b) in zip(got, want):
+        if b.startswith(b"t s;"):
+            h = len(b) - 1024
+            assert a[:h] == b[:h]
+            d = np.frombuffer(a[h:], dtype=np.uint8).astype(int) - np.frombuffer(b[h:], dtype=np.uint8).astype(int)
+            assert np.abs(d).max() <= 1 and (d != 0).mean() < 0.01
+        else:
+            skip = 8 if a.startswith(b"FF;t a;d") else 0
+            assert a[:skip] == b[:skip]
+            assert np.abs(np.frombuffer(a[skip:], dtype="<f4") - np.frombuffer(b[skip:], dtype="<f4")).max() <= 1e-4
