@@ -99,6 +99,7 @@ struct b200_spectrum_plan {
     float db_offset;
     float2* d_twiddle;             // N-point table
     float2* d_twiddle1024;         // 1024-point table (N = 2048 / 4096 / 8192 run M branches of 1024)
+    float2* d_twiddle_rk;          // [M][1024]: W_N^(r k), the layout spectrum_mx1024.cu reads with immediate offsets
     float* d_window;
     Spec64kExtra x64;              // N = 65536 only (all null otherwise)
     int device;
@@ -191,6 +192,7 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
         return nullptr;
     }
     pl->d_twiddle1024 = nullptr;
+    pl->d_twiddle_rk = nullptr;
     memset(&pl->x64, 0, sizeof(pl->x64));
     pl->d_twiddle = upload_twiddles(N);
     const bool wants1024 = (N == 2048 || N == 4096 || N == 8192 || N == 65536);
@@ -212,6 +214,21 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
             cudaFree(pl->d_twiddle);
             if (pl->d_window) cudaFree(pl->d_window);
             delete pl;
+            return nullptr;
+        }
+    }
+    if (N == 2048 || N == 4096 || N == 8192) {
+        const int M = N / 1024;
+        std::vector<float2> trk((size_t) M * 1024);
+        for (int r = 0; r < M; ++r)
+            for (int k = 0; k < 1024; ++k) {
+                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double) (r * k) / (long double) N;
+                trk[(size_t) r * 1024 + k] = make_float2((float) cosl(a), (float) sinl(a));
+            }
+        if (cudaMalloc((void**) &pl->d_twiddle_rk, sizeof(float2) * trk.size()) != cudaSuccess ||
+            cudaMemcpy(pl->d_twiddle_rk, trk.data(), sizeof(float2) * trk.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("spectrum plan: twiddle upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            b200_spectrum_plan_destroy(pl);
             return nullptr;
         }
     }
@@ -251,6 +268,7 @@ void b200_spectrum_plan_destroy(b200_spectrum_plan* plan)
     if (plan == nullptr) return;
     if (plan->d_twiddle) cudaFree(plan->d_twiddle);
     if (plan->d_twiddle1024) cudaFree(plan->d_twiddle1024);
+    if (plan->d_twiddle_rk) cudaFree(plan->d_twiddle_rk);
     if (plan->d_window) cudaFree(plan->d_window);
     if (plan->x64.twiddle_rk) cudaFree((void*) plan->x64.twiddle_rk);
     if (plan->x64.window_rm) cudaFree((void*) plan->x64.window_rm);
@@ -312,7 +330,7 @@ static int spectrum_exec_kind(b200_spectrum_plan* plan, const void* d_in, int64_
             return B200_ERR_ALIGN;
         }
         p.twiddle = plan->d_twiddle1024;
-        p.twiddle_n = plan->d_twiddle;
+        p.twiddle_n = plan->N == 65536 ? plan->d_twiddle : plan->d_twiddle_rk;
         if (plan->N == 65536) return launch_spectrum64k(p, plan->x64, stream);
         return launch_spectrum_mx1024(p, plan->N, stream);
     }

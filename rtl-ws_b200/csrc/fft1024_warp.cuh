@@ -60,12 +60,18 @@ __device__ __forceinline__ void fft1024_load(const uint16_t* in16, const float* 
 // The inter-pass twiddles W_1024^(n2*k1) are applied on the READ side (lane = k1, register
 // n2 -- the table is symmetric, so the same lane-private tw[] serves) fused into pass 2's first
 // butterfly stage.
+// first pass: 32-point transforms over n1 (registers only; no twiddles are applied here)
 template <bool BIASED>
-__device__ __forceinline__ void fft1024_transform(c64 (&a)[32], const float2 (&tw)[32], float2* xch, int lane,
-                                                  c64 (&b)[32])
+__device__ __forceinline__ void fft1024_pass1(c64 (&a)[32])
 {
-    fft_dit32<false>(a, tw);
+    float2 unused[32];
+    fft_dit32<false>(a, unused);
     if (BIASED) a[0] = csub(a[0], cpack(269484032.0f, 269484032.0f));   // 32 * (2^23 + 2^15)
+}
+
+// transpose through xch + second pass; `a` as left by fft1024_pass1
+__device__ __forceinline__ void fft1024_pass2(c64 (&a)[32], const float2 (&tw)[32], float2* xch, int lane, c64 (&b)[32])
+{
     __syncwarp();           // every lane is done reading xch for the previous frame
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1) reinterpret_cast<c64*>(xch)[k1 * FFT1024_XCH_STRIDE + lane] = a[k1];
@@ -77,6 +83,14 @@ __device__ __forceinline__ void fft1024_transform(c64 (&a)[32], const float2 (&t
         b[bitrev<32>(2 * m + 1)] = v.y;
     }
     fft_dit32<true>(b, tw);
+}
+
+template <bool BIASED>
+__device__ __forceinline__ void fft1024_transform(c64 (&a)[32], const float2 (&tw)[32], float2* xch, int lane,
+                                                  c64 (&b)[32])
+{
+    fft1024_pass1<BIASED>(a);
+    fft1024_pass2(a, tw, xch, lane, b);
 }
 
 // transform + |X|^2:  pw[k2] = |X[lane + 32 * k2]|^2 * 2^30 (raw power)

@@ -19,7 +19,7 @@ struct SpecParams {
     uint8_t* db_u8;               // [n_streams][n_rows][N] or null
     float db_offset;              // 10*log10(g / (K * 2^14)): folds gain, /count and the 1/128 input scale
     const float2* twiddle;        // exp(-2*pi*i*k/N), k = 0..N-1 (device); the 1024-point table for N = M * 1024
-    const float2* twiddle_n;      // N-point table when `twiddle` is the 1024-point one, else null
+    const float2* twiddle_n;      // N = 65536: the N-point table; N = M * 1024 <= 8192: [M][1024] W_N^(r k); else null
     const float* window;          // N floats (device) or null = rectangular
 };
 
