@@ -78,6 +78,7 @@ int cached_occupancy(const void* kernel, int block_threads, int smem_bytes)
 // launchers implemented next to their kernels
 int launch_spectrum1024(const SpecParams& p, cudaStream_t stream);
 int launch_spectrum_generic(const SpecParams& p, int N, int kind, cudaStream_t stream);
+int launch_spectrum4096(const SpecParams& p, cudaStream_t stream);
 int launch_spectrum_mx1024(const SpecParams& p, int N, cudaStream_t stream);
 int launch_spectrum64k(const SpecParams& p, const Spec64kExtra& x, cudaStream_t stream);
 int launch_fm_chain(const FmParams& p, cudaStream_t stream);
@@ -100,6 +101,7 @@ struct b200_spectrum_plan {
     float2* d_twiddle;             // N-point table
     float2* d_twiddle1024;         // 1024-point table (N = 2048 / 4096 / 8192 run M branches of 1024)
     float2* d_twiddle_rk;          // [M][1024]: W_N^(r k), the layout spectrum_mx1024.cu reads with immediate offsets
+    float2* d_twiddle_4k;          // N = 4096: [64][64] W_4096^(n2 k1), the inter-pass table of spectrum4096.cu
     float* d_window;
     Spec64kExtra x64;              // N = 65536 only (all null otherwise)
     int device;
@@ -193,6 +195,7 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
     }
     pl->d_twiddle1024 = nullptr;
     pl->d_twiddle_rk = nullptr;
+    pl->d_twiddle_4k = nullptr;
     memset(&pl->x64, 0, sizeof(pl->x64));
     pl->d_twiddle = upload_twiddles(N);
     const bool wants1024 = (N == 2048 || N == 4096 || N == 8192 || N == 65536);
@@ -227,6 +230,20 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
             }
         if (cudaMalloc((void**) &pl->d_twiddle_rk, sizeof(float2) * trk.size()) != cudaSuccess ||
             cudaMemcpy(pl->d_twiddle_rk, trk.data(), sizeof(float2) * trk.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("spectrum plan: twiddle upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            b200_spectrum_plan_destroy(pl);
+            return nullptr;
+        }
+    }
+    if (N == 4096) {
+        std::vector<float2> t4((size_t) 64 * 64);
+        for (int n2 = 0; n2 < 64; ++n2)
+            for (int k1 = 0; k1 < 64; ++k1) {
+                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double) (n2 * k1) / 4096.0L;
+                t4[(size_t) n2 * 64 + k1] = make_float2((float) cosl(a), (float) sinl(a));
+            }
+        if (cudaMalloc((void**) &pl->d_twiddle_4k, sizeof(float2) * t4.size()) != cudaSuccess ||
+            cudaMemcpy(pl->d_twiddle_4k, t4.data(), sizeof(float2) * t4.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
             set_error("spectrum plan: twiddle upload failed: %s", cudaGetErrorString(cudaGetLastError()));
             b200_spectrum_plan_destroy(pl);
             return nullptr;
@@ -269,6 +286,7 @@ void b200_spectrum_plan_destroy(b200_spectrum_plan* plan)
     if (plan->d_twiddle) cudaFree(plan->d_twiddle);
     if (plan->d_twiddle1024) cudaFree(plan->d_twiddle1024);
     if (plan->d_twiddle_rk) cudaFree(plan->d_twiddle_rk);
+    if (plan->d_twiddle_4k) cudaFree(plan->d_twiddle_4k);
     if (plan->d_window) cudaFree(plan->d_window);
     if (plan->x64.twiddle_rk) cudaFree((void*) plan->x64.twiddle_rk);
     if (plan->x64.window_rm) cudaFree((void*) plan->x64.window_rm);
@@ -332,6 +350,10 @@ static int spectrum_exec_kind(b200_spectrum_plan* plan, const void* d_in, int64_
         p.twiddle = plan->d_twiddle1024;
         p.twiddle_n = plan->N == 65536 ? plan->d_twiddle : plan->d_twiddle_rk;
         if (plan->N == 65536) return launch_spectrum64k(p, plan->x64, stream);
+        if (plan->N == 4096) {
+            p.twiddle_n = plan->d_twiddle_4k;
+            return launch_spectrum4096(p, stream);
+        }
         return launch_spectrum_mx1024(p, plan->N, stream);
     }
     return launch_spectrum_generic(p, plan->N, kind, stream);

@@ -238,6 +238,30 @@ __device__ __forceinline__ void fft_dit64(c64 (&a)[64])
     }
 }
 
+// 64-point forward DIT FFT whose input x[n] is first multiplied by tw_col[stride * n] (tw_col[0] taken
+// as 1): the inter-pass twiddles of a 64 x 64 decomposition, read just in time from a table column
+// (coalesced across threads) and fused into the first butterfly stage, so they never occupy more
+// than a few registers.  Input a[p] = x[bitrev<64>(p)], output natural order.
+__device__ __forceinline__ void fft_dit64_pretwiddled(c64 (&a)[64], const float2* __restrict__ tw_col, int stride)
+{
+#pragma unroll
+    for (int g = 0; g < 64; g += 2) {
+        const int na = bitrev<64>(g);
+        const int nb = bitrev<64>(g + 1);
+        const float2 ta = na == 0 ? make_float2(1.0f, 0.0f) : __ldg(tw_col + stride * na);
+        const float2 tb = __ldg(tw_col + stride * nb);
+        dit_butterfly_pretwiddled(a[g], a[g + 1], na == 0, ta, tb);
+    }
+#pragma unroll
+    for (int half = 2; half < 64; half <<= 1) {
+#pragma unroll
+        for (int g = 0; g < 64; g += 2 * half) {
+#pragma unroll
+            for (int k = 0; k < half; ++k) dit_butterfly64(a[g + k], a[g + k + half], k * (32 / half));
+        }
+    }
+}
+
 // In-place forward DIT FFT of R <= 16 points, no pre-twiddles.  Input a[p] = x[bitrev<R>(p)],
 // output natural order.
 template <int R>

@@ -153,6 +153,24 @@ def test_other_frame_lengths(pkg, cuda, po, synth, N, K):
     assert np.array_equal(out["power"][0].argmax(axis=1), want.argmax(axis=1))
 
 
+@pytest.mark.parametrize("N,rows", [(2048, 1300), (4096, 1300), (8192, 330)])
+def test_persistent_loop_many_rows(pkg, cuda, po, synth, N, rows):
+    """More rows than resident CTAs: every CTA walks several frames (TMA ring wrap-around, mbarrier phase
+    flips), K = 1 and K = 2, rectangular and Hann at 50 % overlap; u8 payload bytes included."""
+    torch = cuda
+    iq = synth.s2_tones(N * rows, N=N, seed=N % 89)
+    out = run_plan(pkg, cuda, iq, N=N)
+    want = po.Spectrum(N).rows(iq)
+    assert out["power"].shape == (1, rows, N)
+    check_power(out["power"][0], want)
+    check_db(out["db"][0], want)
+    check_payload(out["db_u8"][0][::97], want[::97], 1, 0, po)
+    out = run_plan(pkg, cuda, iq[:N * 200], N=N, K=2, hop=N // 2, window=pkg.WINDOW_HANN)
+    want = po.Spectrum(N, window=synth.hann(N)).rows(iq[:N * 200], hop=N // 2, K=2)
+    check_power(out["power"][0], want)
+    check_db(out["db"][0], want, K=2)
+
+
 def test_goldens_n4096_n65536(pkg, cuda, synth):
     g = np.load(os.path.join(GOLD, "spectrum_n4096.npz"))
     out = run_plan(pkg, cuda, g["iq"], N=4096, K=3)

@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python tools/kbench.py --only spectrum4096_db --streams 256
-python tools/kbench.py --only spectrum2048_db --streams 256
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python tools/kbench.py --streams 256 > gpurun_out/s5_kbench.log 2>&1; cat gpurun_out/s5_kbench.log
