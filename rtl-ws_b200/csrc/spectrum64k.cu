@@ -25,8 +25,8 @@ namespace b200 {
 namespace {
 
 constexpr int N64K = 65536;
-constexpr int S64_THREADS = 320;
-constexpr int S64_WARPS = 10;                                             // 128 KB frame + 10 exchange tiles = 218 KB
+constexpr int S64_THREADS = 256;
+constexpr int S64_WARPS = 8;                                              // 64 branches and 1024 columns divide evenly
 constexpr int S64_FRAME_BYTES = 2 * N64K;                                  // 131072
 constexpr int S64_SMEM = S64_FRAME_BYTES + S64_WARPS * FFT1024_XCH_BYTES + 16;
 

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python tools/kbench.py --streams 256 > gpurun_out/s5_kbench.log 2>&1; cat gpurun_out/s5_kbench.log
+python -m pytest tests/test_gpu_spectrum.py -x -q -k "65536" 2>&1 | tail -3
+python tools/kbench.py --only spectrum65536_hann_50pct --streams 256
