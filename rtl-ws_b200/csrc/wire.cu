@@ -122,6 +122,10 @@ int stage_reserve(HeaderStage& st, int n)
     if (st.h_len) cudaFreeHost(st.h_len);
     if (st.d) cudaFree(st.d);
     if (st.d_len) cudaFree(st.d_len);
+    if (st.done && st.dev != dev) {          // an event belongs to the device it was created on
+        cudaEventDestroy(st.done);
+        st.done = nullptr;
+    }
     st.h = st.d = nullptr;
     st.h_len = st.d_len = nullptr;
     st.cap = 0;
