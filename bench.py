@@ -391,10 +391,17 @@ def main():
                 "traffic": None, "kernel": "chain_fused_kernel (b200_chain_exec: 1024-pt spectra + FM branch, one pass over the IQ)",
                 "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
+    # DRAM bytes per launch from the committed ncu capture of this kernel (profiles/traffic.json): the capture
+    # is of the N = 1 default workload; other shapes get its measured bytes-per-sample times their samples
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("chain_traffic_bytes_per_launch")
+            cap = json.load(open(prof))
+            if cap.get("samples_per_launch") == n_local * L:
+                roofline["traffic"] = cap.get("chain_traffic_bytes_per_launch")
+            elif cap.get("dram_bytes_per_sample"):
+                roofline["traffic"] = int(cap["dram_bytes_per_sample"] * n_local * L)
+                roofline["traffic_note"] = "scaled from the N = 1 capture by samples per launch"
         except Exception:
             pass
 
