@@ -66,7 +66,7 @@ typedef struct b200_spectrum_plan b200_spectrum_plan;
 #define B200_WINDOW_RECT 0   /* the reference */
 #define B200_WINDOW_HANN 1   /* periodic Hann, extension */
 
-/* N: a power of two in [16, 65536] (1024 has a specialised kernel).  gain_db follows cbb_main.c:112 (integer division by 10). */
+/* N: a power of two in [16, 65536] (1024, 2048, 4096, 8192 and 65536 have specialised kernels).  gain_db follows cbb_main.c:112 (integer division by 10). */
 b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row_hop, int window, int gain_db);
 void b200_spectrum_plan_destroy(b200_spectrum_plan* plan);
 /* Rows that fit in a stream of n_samples. */

@@ -39,6 +39,7 @@ constexpr int S4K_TILE_STRIDE = 66;                                  // complex 
 constexpr int S4K_TILE_BYTES = 64 * S4K_TILE_STRIDE * 8;             // 33792
 constexpr int S4K_BAR_OFFSET = S4K_STAGES * S4K_FRAME_BYTES + S4K_TILE_BYTES;
 constexpr int S4K_SMEM = S4K_BAR_OFFSET + 64;
+constexpr int S4K_PRE = 8;                                           // first-stage butterflies whose twiddles are fetched early
 constexpr int S4K_CTAS_PER_SM = 4;     // 8 warps per SM, up to 255 registers (the next step, 12 warps, would mean 168 and spills)
 
 // pw[k2] = raw power of bin t + 64*k2 -> the requested arrays, display order: col = t + 64*((k2 + 32) & 63).
@@ -163,6 +164,9 @@ __global__ void __launch_bounds__(S4K_THREADS, S4K_CTAS_PER_SM) spectrum4096_ker
             for (int k1 = 0; k1 < 64; ++k1) tile[k1 * S4K_TILE_STRIDE + t] = a[k1];
             __syncwarp();
             if (lane == 0) mbar_arrive(tfull);
+            // the column registers are dead now: fetch the first twiddle rows while the other warp catches up
+            float2 pre[2 * S4K_PRE + 1];
+            fft_dit64_prefetch<S4K_PRE>(pre, twcol, 64);
             mbar_wait(tfull, f & 1);
             if (t == 0 && f + S4K_STAGES < n_frames) {        // both warps have consumed the stage
                 fence_proxy_async_smem();
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(S4K_THREADS, S4K_CTAS_PER_SM) spectrum4096_ker
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(tdone);
-            fft_dit64_pretwiddled(b, twcol, 64);
+            fft_dit64_pretwiddled<S4K_PRE>(b, pre, twcol, 64);
 
             float pw[64];
 #pragma unroll
