@@ -240,38 +240,17 @@ __device__ __forceinline__ void fft_dit64(c64 (&a)[64])
 
 // 64-point forward DIT FFT whose input x[n] is first multiplied by tw_col[stride * n] (tw_col[0] taken
 // as 1): the inter-pass twiddles of a 64 x 64 decomposition, read just in time from a table column
-// (coalesced across threads) and fused into the first butterfly stage, so they never occupy more
-// than a few registers.  The twiddles of the first PRE butterflies can be fetched ahead of time
-// (fft_dit64_prefetch, e.g. while waiting for the data) so that their latency is not exposed.
+// (shared memory; consecutive threads read consecutive entries) and fused into the first butterfly
+// stage, so they never occupy more than a few registers.
 // Input a[p] = x[bitrev<64>(p)], output natural order.
-template <int PRE>
-__device__ __forceinline__ void fft_dit64_prefetch(float2 (&pre)[2 * PRE + 1], const float2* __restrict__ tw_col, int stride)
-{
-#pragma unroll
-    for (int i = 0; i < PRE; ++i) {
-        const int na = bitrev<64>(2 * i);
-        const int nb = bitrev<64>(2 * i + 1);
-        pre[2 * i] = na == 0 ? make_float2(1.0f, 0.0f) : __ldg(tw_col + stride * na);
-        pre[2 * i + 1] = __ldg(tw_col + stride * nb);
-    }
-}
-
-template <int PRE>
-__device__ __forceinline__ void fft_dit64_pretwiddled(c64 (&a)[64], const float2 (&pre)[2 * PRE + 1],
-                                                      const float2* __restrict__ tw_col, int stride)
+__device__ __forceinline__ void fft_dit64_pretwiddled(c64 (&a)[64], const float2* tw_col, int stride)
 {
 #pragma unroll
     for (int g = 0; g < 64; g += 2) {
         const int na = bitrev<64>(g);
         const int nb = bitrev<64>(g + 1);
-        float2 ta, tb;
-        if (g / 2 < PRE) {
-            ta = pre[g];
-            tb = pre[g + 1];
-        } else {
-            ta = na == 0 ? make_float2(1.0f, 0.0f) : __ldg(tw_col + stride * na);
-            tb = __ldg(tw_col + stride * nb);
-        }
+        const float2 ta = na == 0 ? make_float2(1.0f, 0.0f) : tw_col[stride * na];
+        const float2 tb = tw_col[stride * nb];
         dit_butterfly_pretwiddled(a[g], a[g + 1], na == 0, ta, tb);
     }
 #pragma unroll

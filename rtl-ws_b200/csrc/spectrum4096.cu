@@ -4,20 +4,24 @@
 // 4096 = 64 x 64 with n = 64*n1 + n2, k = k1 + 64*k2:
 //   pass 1: thread n2 (0..63) holds x[64*n1 + n2] (n1 = 0..63) in registers and runs a 64-point
 //           FFT over n1 (fft_dit64: 128 registers of data);
-//   one exchange through a padded shared tile (row stride 66 complex: the 64-bit column
-//           stores and the 128-bit row loads are both conflict-free);
-//   pass 2: thread k1 reads its row, multiplies by W_4096^(n2*k1) -- read just in time from a
-//           [n2][k1] table, one coalesced 512-byte row per n2, fused into the first butterfly
-//           stage -- and runs a 64-point FFT over n2: bins k1 + 64*k2.
+//   one exchange through a shared tile (unpadded, XOR-swizzled: the 64-bit column stores and the
+//           128-bit row loads are both conflict-free);
+//   pass 2: thread k1 reads its row, multiplies by W_4096^(n2*k1) -- a [n2][k1] table the CTA
+//           keeps in shared memory, fused into the first butterfly stage -- and runs a 64-point
+//           FFT over n2: bins k1 + 64*k2, so a warp store is 128 contiguous bytes.
 // Against running four 1024-point branch transforms and a radix-4 combine (spectrum_mx1024.cu)
-// this needs ONE shared-memory round trip per point instead of two (the 1-D tile exchange is
-// what saturates first there: 346 shared wavefronts per 1024 points against 223 here) and about
-// a quarter fewer instructions per sample.
+// this needs ONE shared-memory round trip per point instead of two (the exchange traffic is what
+// saturates first there: 346 shared wavefronts per 1024 points against 232 here) and about 30 %
+// fewer instructions per sample.
 //
-// The two warps of a frame meet twice per frame on mbarriers: `tfull` once both have stored
-// their pass-1 columns, and `tdone` -- on which they arrive as soon as their rows are in
-// registers and wait only before the NEXT frame's column stores, a whole second pass, epilogue,
-// gather and first pass later.  Frames arrive by TMA bulk copies into a ring.
+// One CTA per SM holds FOUR independent frame pairs (own ring, own tile, own barriers) that share
+// the 32 KB twiddle table: with the table in global memory (two-warp CTAs) ncu showed it missing
+// L1 -- 28 KB is all that is left next to 200 KB of shared memory -- and the second pass starting
+// on L2 latency (585 Gsamples/s; 675 with the table in shared memory).
+// The two warps of a frame meet twice per frame on mbarriers: `tfull` once both have stored their
+// pass-1 columns, and `tdone` -- on which they arrive as soon as their rows are in registers and
+// wait only before the NEXT frame's column stores, a whole second pass, epilogue, gather and first
+// pass later.  Frames arrive by TMA bulk copies into a two-deep ring per pair.
 //
 // Reference arithmetic per frame as in spectrum1024.cu: spectrum.c:54-58 (unpack), :21 (forward
 // DFT), :23-34 (fftshift, |X|^2, accumulate, DC-position patch), cbb_main.c:112-128 (dB, u8).
@@ -32,15 +36,26 @@ namespace b200 {
 namespace {
 
 constexpr int N4K = 4096;
-constexpr int S4K_THREADS = 64;
+constexpr int S4K_PAIRS = 4;                                         // frame pairs (2 warps each) per CTA
+constexpr int S4K_THREADS = 64 * S4K_PAIRS;
 constexpr int S4K_FRAME_BYTES = 2 * N4K;
 constexpr int S4K_STAGES = 2;
-constexpr int S4K_TILE_STRIDE = 66;                                  // complex per row
-constexpr int S4K_TILE_BYTES = 64 * S4K_TILE_STRIDE * 8;             // 33792
-constexpr int S4K_BAR_OFFSET = S4K_STAGES * S4K_FRAME_BYTES + S4K_TILE_BYTES;
-constexpr int S4K_SMEM = S4K_BAR_OFFSET + 64;
-constexpr int S4K_PRE = 8;                                           // first-stage butterflies whose twiddles are fetched early
-constexpr int S4K_CTAS_PER_SM = 4;     // 8 warps per SM, up to 255 registers (the next step, 12 warps, would mean 168 and spills)
+constexpr int S4K_TILE_BYTES = 64 * 64 * 8;                          // 32768: unpadded, XOR-swizzled (see tile_col)
+constexpr int S4K_TW_BYTES = 64 * 64 * 8;                            // the [n2][k1] inter-pass twiddle table
+constexpr int S4K_PAIR_BYTES = S4K_STAGES * S4K_FRAME_BYTES + S4K_TILE_BYTES;
+constexpr int S4K_BAR_OFFSET = S4K_TW_BYTES + S4K_PAIRS * S4K_PAIR_BYTES;
+constexpr int S4K_BAR_BYTES = 64;                                    // per pair: full[2], tfull, tdone
+constexpr int S4K_SMEM = S4K_BAR_OFFSET + S4K_PAIRS * S4K_BAR_BYTES;  // 229632 of the 232448 a CTA may have
+
+// Exchange-tile column of element (row, col): columns are XOR-ed with 2 * (row mod 8).  A column store
+// (fixed row, 32 consecutive cols) stays a permutation of 32 consecutive 8-byte slots; a 128-bit row
+// load (32 consecutive rows, the pair 2m, 2m+1) lands its 8 lanes per quarter-warp on 8 different
+// 16-byte slots.  Both conflict-free without padding, which is what lets four tiles, four two-deep
+// rings and the twiddle table share one SM.
+__device__ __forceinline__ int tile_col(int row, int col)
+{
+    return col ^ (2 * (row & 7));
+}
 
 // pw[k2] = raw power of bin t + 64*k2 -> the requested arrays, display order: col = t + 64*((k2 + 32) & 63).
 // `base` = row * 4096 + t.  dc: the value for display index 2048 (written by thread 63 only).
@@ -79,24 +94,28 @@ __device__ __forceinline__ void store_row4096(const SpecParams& p, float dboff, 
 }
 
 template <bool WINDOW, bool MULTI>
-__global__ void __launch_bounds__(S4K_THREADS, S4K_CTAS_PER_SM) spectrum4096_kernel(const SpecParams p)
+__global__ void __launch_bounds__(S4K_THREADS, 1) spectrum4096_kernel(const SpecParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int t = threadIdx.x;
+    const int pair = threadIdx.x >> 6;
+    const int t = threadIdx.x & 63;
     const int lane = t & 31;
-    uint8_t* ring = smem;
-    c64* tile = reinterpret_cast<c64*>(smem + S4K_STAGES * S4K_FRAME_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S4K_BAR_OFFSET);
+    float2* tws = reinterpret_cast<float2*>(smem);                                  // [n2][k1]
+    uint8_t* ring = smem + S4K_TW_BYTES + pair * S4K_PAIR_BYTES;
+    c64* tile = reinterpret_cast<c64*>(ring + S4K_STAGES * S4K_FRAME_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S4K_BAR_OFFSET + pair * S4K_BAR_BYTES);
     uint64_t* tfull = full + S4K_STAGES;
     uint64_t* tdone = tfull + 1;
 
     const uint32_t total_items = (uint32_t) p.n_streams * (uint32_t) p.n_rows;
     const uint32_t n_rows = (uint32_t) p.n_rows;
     const int K = MULTI ? p.K : 1;
-    if (blockIdx.x >= total_items) return;
-    const uint32_t n_items = (total_items - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const uint32_t first = blockIdx.x * S4K_PAIRS + pair;              // pairs stride over rows like CTAs would
+    const uint32_t stride = gridDim.x * S4K_PAIRS;
+    const uint32_t n_items = first < total_items ? (total_items - first + stride - 1) / stride : 0;
     const uint32_t n_frames = n_items * (uint32_t) K;
 
+    for (int i = threadIdx.x; i < 64 * 64; i += S4K_THREADS) tws[i] = __ldg(p.twiddle_n + i);
     if (t == 0) {
 #pragma unroll
         for (int i = 0; i < S4K_STAGES; ++i) mbar_init(&full[i], 1);
@@ -107,7 +126,7 @@ __global__ void __launch_bounds__(S4K_THREADS, S4K_CTAS_PER_SM) spectrum4096_ker
     __syncthreads();
 
     auto frame_src = [&](uint32_t f) -> const uint8_t* {
-        const uint32_t item = blockIdx.x + (f / (uint32_t) K) * gridDim.x;
+        const uint32_t item = first + (f / (uint32_t) K) * stride;
         const uint32_t j = f % (uint32_t) K;
         const uint32_t s = item / n_rows;
         const uint32_t row = item - s * n_rows;
@@ -120,7 +139,7 @@ __global__ void __launch_bounds__(S4K_THREADS, S4K_CTAS_PER_SM) spectrum4096_ker
         }
     }
 
-    const float2* twcol = p.twiddle_n + t;                    // W_4096^(n2 * t) at [n2][t]
+    const float2* twcol = tws + t;                            // W_4096^(n2 * t) at [n2][t]
     const float dboff = p.db_offset - 16.0f * DB_PER_LOG2;
 
     float acc[64];          // MULTI only (dead otherwise)
@@ -132,7 +151,7 @@ __global__ void __launch_bounds__(S4K_THREADS, S4K_CTAS_PER_SM) spectrum4096_ker
 
     uint32_t f = 0;
     for (uint32_t it = 0; it < n_items; ++it) {
-        const uint32_t item = blockIdx.x + it * gridDim.x;
+        const uint32_t item = first + it * stride;
         const size_t out_base = (size_t) item * N4K + (size_t) t;
         for (int j = 0; j < K; ++j, ++f) {
             const int st = f % S4K_STAGES;
@@ -161,12 +180,9 @@ __global__ void __launch_bounds__(S4K_THREADS, S4K_CTAS_PER_SM) spectrum4096_ker
 
             if (f > 0) mbar_wait(tdone, (f - 1) & 1);         // both warps hold their rows of frame f - 1
 #pragma unroll
-            for (int k1 = 0; k1 < 64; ++k1) tile[k1 * S4K_TILE_STRIDE + t] = a[k1];
+            for (int k1 = 0; k1 < 64; ++k1) tile[k1 * 64 + tile_col(k1, t)] = a[k1];
             __syncwarp();
             if (lane == 0) mbar_arrive(tfull);
-            // the column registers are dead now: fetch the first twiddle rows while the other warp catches up
-            float2 pre[2 * S4K_PRE + 1];
-            fft_dit64_prefetch<S4K_PRE>(pre, twcol, 64);
             mbar_wait(tfull, f & 1);
             if (t == 0 && f + S4K_STAGES < n_frames) {        // both warps have consumed the stage
                 fence_proxy_async_smem();
@@ -178,13 +194,13 @@ __global__ void __launch_bounds__(S4K_THREADS, S4K_CTAS_PER_SM) spectrum4096_ker
             c64 b[64];
 #pragma unroll
             for (int m = 0; m < 32; ++m) {
-                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&tile[t * S4K_TILE_STRIDE + 2 * m]);
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&tile[t * 64 + tile_col(t, 2 * m)]);
                 b[bitrev<64>(2 * m)] = v.x;
                 b[bitrev<64>(2 * m + 1)] = v.y;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(tdone);
-            fft_dit64_pretwiddled<S4K_PRE>(b, pre, twcol, 64);
+            fft_dit64_pretwiddled(b, twcol, 64);
 
             float pw[64];
 #pragma unroll
@@ -224,9 +240,9 @@ int launch_spectrum4096(const SpecParams& p, cudaStream_t stream)
     auto kern = p.K > 1 ? (p.window ? spectrum4096_kernel<true, true> : spectrum4096_kernel<false, true>)
                         : (p.window ? spectrum4096_kernel<true, false> : spectrum4096_kernel<false, false>);
     if (int rc = ensure_dynamic_smem((const void*) kern, S4K_SMEM)) return rc;
-    const int ctas_per_sm = cached_occupancy((const void*) kern, S4K_THREADS, S4K_SMEM);
-    uint64_t grid = (uint64_t) sm_count() * (uint64_t) ctas_per_sm;
-    if (grid > total) grid = total;
+    uint64_t grid = (uint64_t) sm_count();                     // one CTA of four frame pairs per SM
+    const uint64_t needed = (total + S4K_PAIRS - 1) / S4K_PAIRS;
+    if (grid > needed) grid = needed;
     kern<<<(unsigned) grid, S4K_THREADS, S4K_SMEM, stream>>>(p);
     B200_LAUNCH_CHECK();
     return B200_OK;

@@ -38,6 +38,8 @@ db4k = torch.empty((S, L // 4096, 4096), dtype=torch.float32, device="cuda")
 plan64k = pkg.SpectrumPlan(65536, hop=32768, window=pkg.WINDOW_HANN)
 rows64k = plan64k.rows(L)
 db64k = torch.empty((S, rows64k, 65536), dtype=torch.float32, device="cuda")
+plan1k_h = pkg.SpectrumPlan(1024, window=pkg.WINDOW_HANN)
+plan4k_h = pkg.SpectrumPlan(4096, window=pkg.WINDOW_HANN)
 plan2k = pkg.SpectrumPlan(2048)
 db2k = torch.empty((S, L // 2048, 2048), dtype=torch.float32, device="cuda")
 
@@ -47,6 +49,8 @@ cases = {
     "fm_chain": (lambda: pkg.fm_exec(ring, audio=audio), 2.1),
     "chain_fused": (lambda: pkg.chain_exec(ring, db=db, audio=audio), 6.1),
     "spectrum4096_db": (lambda: plan4k.exec(ring.batch, db=True, out={"db": db4k}), 6.0),
+    "spectrum1024_hann_db": (lambda: plan1k_h.exec(ring.batch, db=True, out=out), 6.0),
+    "spectrum4096_hann_db": (lambda: plan4k_h.exec(ring.batch, db=True, out={"db": db4k}), 6.0),
     "spectrum2048_db": (lambda: plan2k.exec(ring.batch, db=True, out={"db": db2k}), 6.0),
     "spectrum65536_hann_50pct": (lambda: plan64k.exec(ring.batch, db=True, out={"db": db64k}), 10.0),
 }
