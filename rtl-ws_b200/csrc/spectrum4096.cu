@@ -140,6 +140,12 @@ __global__ void __launch_bounds__(S4K_THREADS, 1) spectrum4096_kernel(const Spec
     }
 
     const float2* twcol = tws + t;                            // W_4096^(n2 * t) at [n2][t]
+    // The periodic Hann window of sample 64*n1 + t, without a table:  w = 1/2 - 1/2 cos(2 pi (64 n1 + t) / 4096)
+    //   = 1/2 - 1/2 (cos(2 pi n1 / 64) * ct - sin(2 pi n1 / 64) * st),  ct, st = cos, sin(2 pi t / 4096):
+    // two FMAs with compile-time coefficients per sample (a 16 KB table next to 224 KB of shared memory would
+    // come from L2 every time: 521 Gsamples/s with the table, measured).
+    float ct = 1.0f, st = 0.0f;
+    if (WINDOW) sincospif((float) t * (1.0f / 2048.0f), &st, &ct);
     const float dboff = p.db_offset - 16.0f * DB_PER_LOG2;
 
     float acc[64];          // MULTI only (dead otherwise)
@@ -154,9 +160,9 @@ __global__ void __launch_bounds__(S4K_THREADS, 1) spectrum4096_kernel(const Spec
         const uint32_t item = first + it * stride;
         const size_t out_base = (size_t) item * N4K + (size_t) t;
         for (int j = 0; j < K; ++j, ++f) {
-            const int st = f % S4K_STAGES;
-            mbar_wait(&full[st], (f / S4K_STAGES) & 1);
-            const uint16_t* in16 = reinterpret_cast<const uint16_t*>(ring + st * S4K_FRAME_BYTES);
+            const int stage = f % S4K_STAGES;
+            mbar_wait(&full[stage], (f / S4K_STAGES) & 1);
+            const uint16_t* in16 = reinterpret_cast<const uint16_t*>(ring + stage * S4K_FRAME_BYTES);
 
             // ---- pass 1: column t, samples 64*n1 + t ----
             c64 a[64];
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(S4K_THREADS, 1) spectrum4096_kernel(const Spec
                     a[q] = cpack(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7504)),
                                  __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7514)));
                     if (WINDOW) {
-                        const float w = __ldg(&p.window[64 * n1 + t]);
+                        const float w = fmaf(0.5f * sin64(n1), st, fmaf(-0.5f * cos64(n1), ct, 0.5f));
                         a[q] = cmul2(csub(a[q], bias1), cpack(w, w));
                     }
                 }
@@ -186,8 +192,8 @@ __global__ void __launch_bounds__(S4K_THREADS, 1) spectrum4096_kernel(const Spec
             mbar_wait(tfull, f & 1);
             if (t == 0 && f + S4K_STAGES < n_frames) {        // both warps have consumed the stage
                 fence_proxy_async_smem();
-                mbar_arrive_expect_tx(&full[st], S4K_FRAME_BYTES);
-                tma_load_1d(ring + st * S4K_FRAME_BYTES, frame_src(f + S4K_STAGES), S4K_FRAME_BYTES, &full[st]);
+                mbar_arrive_expect_tx(&full[stage], S4K_FRAME_BYTES);
+                tma_load_1d(ring + stage * S4K_FRAME_BYTES, frame_src(f + S4K_STAGES), S4K_FRAME_BYTES, &full[stage]);
             }
 
             // ---- pass 2: row t ----
@@ -228,7 +234,8 @@ __global__ void __launch_bounds__(S4K_THREADS, 1) spectrum4096_kernel(const Spec
 
 }  // namespace
 
-// N = 4096, cmplx_u8 input.  p.twiddle_n must be the [64][64] table W_4096^(n2 * k1).
+// N = 4096, cmplx_u8 input.  p.twiddle_n must be the [64][64] table W_4096^(n2 * k1).  A non-null p.window
+// means the periodic Hann window (the only one b200_spectrum_plan_create offers); the kernel computes it.
 int launch_spectrum4096(const SpecParams& p, cudaStream_t stream)
 {
     const uint64_t total = (uint64_t) p.n_streams * (uint64_t) p.n_rows;
