@@ -60,7 +60,17 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
         }
     };
 
-    for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+    // A CTA takes a CONTIGUOUS range of (stream, row) items, so that with 50 % overlap (hop = N/2, the
+    // spectrogram of BASELINE config 4) consecutive frames share half their samples and only the new half is
+    // fetched: logical row m of the frame lives in physical row m ^ flip, flip alternating between 0 and 512
+    // (the swizzle depends on m mod 32 only, which the flip leaves alone).
+    const int64_t per_cta = (total + gridDim.x - 1) / gridDim.x;
+    const int64_t item_begin = (int64_t) blockIdx.x * per_cta;
+    const int64_t item_end = item_begin + per_cta < total ? item_begin + per_cta : total;
+    const uint8_t* resident = nullptr;      // global address of the frame now in shared memory
+    int flip = 0;
+
+    for (int64_t item = item_begin; item < item_end; ++item) {
         const int64_t s = item / p.n_rows;
         const int64_t row = item - s * p.n_rows;
         const size_t row_base = (size_t) item * N64K;
@@ -68,14 +78,19 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
 
         for (int j = 0; j < K; ++j) {
             // ---- 0. frame -> shared memory, rows word-swizzled by (m mod 32) ----
-            const uint4* src = reinterpret_cast<const uint4*>(p.iq + s * p.stream_stride_bytes +
-                                                              2 * (row * p.row_hop + (int64_t) j * p.hop));
+            const uint8_t* frame = p.iq + s * p.stream_stride_bytes + 2 * (row * p.row_hop + (int64_t) j * p.hop);
+            const bool half = resident != nullptr && frame == resident + S64_FRAME_BYTES / 2;
+            if (half) flip ^= 512;          // the old second half is the new first half
+            else flip = 0;
+            resident = frame;
+            const uint4* src = reinterpret_cast<const uint4*>(frame);
+            const int i0 = half ? S64_FRAME_BYTES / 32 : 0;
 #pragma unroll 4
-            for (int i = tid; i < S64_FRAME_BYTES / 16; i += S64_THREADS) {
+            for (int i = i0 + tid; i < S64_FRAME_BYTES / 16; i += S64_THREADS) {
                 const uint4 v = __ldg(src + i);
                 const int m = i >> 3;
                 const int w0 = (i & 7) * 4;
-                uint32_t* dst = frame32 + m * 32;
+                uint32_t* dst = frame32 + (m ^ flip) * 32;
                 const int sw = m & 31;
                 dst[(w0 + 0) ^ sw] = v.x;
                 dst[(w0 + 1) ^ sw] = v.y;
@@ -90,18 +105,27 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
             fft1024_load_twiddles(p.twiddle, lane, tw);
             for (int r = warp; r < 64; r += S64_WARPS) {
                 c64 a[32];
+                // Hann window of sample 64*(32*n1 + lane) + r without a table:
+                //   w = 1/2 - 1/2 cos(2 pi n1 / 32 + phi),  phi = 2 pi (64 lane + r) / 65536
+                // (the [r][m] window table cost 256 KB of L2 reads per frame per SM)
+                float cphi = 1.0f, sphi = 0.0f;
+                if (WINDOW) sincospif((float) (64 * lane + r) * (1.0f / 32768.0f), &sphi, &cphi);
                 {
                     const c64 bias1 = cpack(8421376.0f, 8421376.0f);        // 2^23 + 256 * 128
-                    const uint8_t* fb = reinterpret_cast<const uint8_t*>(frame32);
+                    // rows m < 512 (n1 < 16) and m >= 512 sit in the halves chosen by `flip`: two base pointers,
+                    // every load still base + compile-time offset
+                    const uint8_t* fb_lo = reinterpret_cast<const uint8_t*>(frame32) + flip * 128;
+                    const uint8_t* fb_hi = reinterpret_cast<const uint8_t*>(frame32) - flip * 128;
 #pragma unroll
                     for (int n1 = 0; n1 < 32; ++n1) {
                         const int m = 32 * n1 + lane;                       // m mod 32 == lane
+                        const uint8_t* fb = n1 < 16 ? fb_lo : fb_hi;
                         const uint32_t v = *reinterpret_cast<const uint16_t*>(fb + m * 128 + (((r >> 1) ^ lane) << 2) + ((r & 1) << 1));
                         const int q = bitrev<32>(n1);
                         a[q] = cpack(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7504)),
                                      __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7514)));
                         if (WINDOW) {
-                            const float w = __ldg(&x.window_rm[r * 1024 + m]);
+                            const float w = fmaf(0.5f * sin32(n1), sphi, fmaf(-0.5f * cos32(n1), cphi, 0.5f));
                             a[q] = cmul2(csub(a[q], bias1), cpack(w, w));
                         }
                     }
