@@ -259,15 +259,6 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
             }
         bool ok = cudaMalloc((void**) &pl->x64.twiddle_rk, sizeof(float2) * trk.size()) == cudaSuccess &&
                   cudaMemcpy((void*) pl->x64.twiddle_rk, trk.data(), sizeof(float2) * trk.size(), cudaMemcpyHostToDevice) == cudaSuccess;
-        if (ok && window == B200_WINDOW_HANN) {
-            std::vector<float> wrm((size_t) 65536);
-            for (int r = 0; r < 64; ++r)
-                for (int m = 0; m < 1024; ++m)
-                    wrm[(size_t) r * 1024 + m] = (float) (0.5L - 0.5L * cosl(2.0L * 3.14159265358979323846264338327950288L *
-                                                                             (long double) (64 * m + r) / 65536.0L));
-            ok = cudaMalloc((void**) &pl->x64.window_rm, sizeof(float) * wrm.size()) == cudaSuccess &&
-                 cudaMemcpy((void*) pl->x64.window_rm, wrm.data(), sizeof(float) * wrm.size(), cudaMemcpyHostToDevice) == cudaSuccess;
-        }
         pl->x64.scratch_ctas = sm_count();
         ok = ok && cudaMalloc((void**) &pl->x64.scratch, sizeof(float2) * 65536 * (size_t) pl->x64.scratch_ctas) == cudaSuccess;
         if (ok && K > 1) ok = cudaMalloc((void**) &pl->x64.acc, sizeof(float) * 65536 * (size_t) pl->x64.scratch_ctas) == cudaSuccess;
@@ -289,7 +280,6 @@ void b200_spectrum_plan_destroy(b200_spectrum_plan* plan)
     if (plan->d_twiddle_4k) cudaFree(plan->d_twiddle_4k);
     if (plan->d_window) cudaFree(plan->d_window);
     if (plan->x64.twiddle_rk) cudaFree((void*) plan->x64.twiddle_rk);
-    if (plan->x64.window_rm) cudaFree((void*) plan->x64.window_rm);
     if (plan->x64.scratch) cudaFree(plan->x64.scratch);
     if (plan->x64.acc) cudaFree(plan->x64.acc);
     delete plan;

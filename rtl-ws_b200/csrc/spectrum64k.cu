@@ -4,18 +4,20 @@
 //
 // 65536 = 64 x 1024, decimation in time by 64:
 //   X[k + 1024 q] = sum_{r<64} W_64^(r q) * ( W_N^(r k) * F_r[k] ),   F_r = FFT_1024( x[64 m + r] ).
-// A CTA (10 warps, one per SM) owns one frame at a time:
+// A CTA (8 warps, one per SM) owns one frame at a time:
 //   0. the 128 KB of IQ bytes are copied into shared memory with 128-bit loads; every 128-byte
 //      row (one m, all 64 r) is word-swizzled by (m mod 32) so that the stride-128-byte reads
 //      of a polyphase branch hit 32 different banks;
-//   1. warp w runs the 32x32 register transform (fft1024_warp.cuh) on branches r = w, w+10, ...,
+//   1. warp w runs the 32x32 register transform (fft1024_warp.cuh) on branches r = w, w+8, ...,
 //      multiplies by W_N^(r k) (table stored [r][k], read coalesced) and writes Z[r][k] to this
-//      CTA's 512 KB slice of a global scratch that stays in the 126 MB L2;
-//   2. block barrier; thread t takes k = t, t+320, ... (< 1024): 64 coalesced loads of Z[.][k],
+//      CTA's 512 KB slice of a global scratch meant to stay in the 126 MB L2 (ncu: most of it does
+//      not -- see DESIGN.md section 4.6);
+//   2. block barrier; thread t takes k = t, t+256, ... (< 1024): 64 coalesced loads of Z[.][k],
 //      a 64-point FFT in registers, |X|^2, K-frame accumulation with the cumulative
 //      DC-position patch (spectrum.c:30-33), dB / power / u8, coalesced stores.
 // Arithmetic per frame as in spectrum1024.cu (spectrum.c:15-58, cbb_main.c:112-128); the window
-// (an extension; the reference is rectangular) is read from a table stored [r][m].
+// (an extension; the reference is rectangular; periodic Hann is the only one the plan offers) is
+// computed, not tabulated.
 #include "b200_common.cuh"
 #include "fft1024_warp.cuh"
 #include "spectrum_kernels.cuh"
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
             }
             __syncthreads();
 
-            // ---- 1. polyphase branches r = warp, warp + 10, ...  (the lane-private inter-pass twiddles
+            // ---- 1. polyphase branches r = warp, warp + 8, ...  (the lane-private inter-pass twiddles
             //         are re-read per frame so that they are not live during phase 2) ----
             float2 tw[32];
             fft1024_load_twiddles(p.twiddle, lane, tw);

@@ -28,7 +28,6 @@ struct Spec64kExtra {
     float2* scratch;              // [scratch_ctas][64][1024] complex: Z[r][k], L2-resident
     float* acc;                   // [scratch_ctas][65536] power accumulators (K > 1), else null
     const float2* twiddle_rk;     // [64][1024]: exp(-2*pi*i*r*k/65536)
-    const float* window_rm;       // [64][1024]: window[64*m + r], or null
     int scratch_ctas;
 };
 
