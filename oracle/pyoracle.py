@@ -26,6 +26,7 @@ REF_BENCH = os.path.join(HERE, "_ref", "ref_bench")
 # the reference's own glue (cbb_main.c, audio_main.c, signal_source.c) linked against the PRODUCT
 # library instead of the reference's spectrum.o / resample.o / rf_decimator.o
 DROPIN_SO = os.path.join(HERE, "_ref", "libdropin_rtlws.so")
+REPLAY_SO = os.path.join(HERE, "_ref", "libreplay_rtlws.so")     # reference signal_source.c over libb200replay.so
 PRODUCT_SO = os.path.join(os.path.dirname(HERE), "rtl-ws_b200", "libb200sdr.so")
 
 HALF_BAND_N = 11

@@ -6,7 +6,7 @@ generators used by the tests and the benchmark.  The directory name carries a hy
 import it through ``__graft_entry__.load_package()`` (tests/conftest.py does) under the
 module name ``rtl_ws_b200``.
 """
-from . import binding, sharding, synth, wire  # noqa: F401
+from . import binding, replay, sharding, synth, wire  # noqa: F401
 from .binding import (  # noqa: F401
     B200Error, SpectrumPlan, StreamRing, Session, PushStream, RfDecimator, CicDelayLine,
     fm_exec, chain_exec, init, lib, launch_count,
