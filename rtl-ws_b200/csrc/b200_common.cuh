@@ -109,6 +109,12 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
         : "memory");
 }
 
+// drop a 128-byte line from L2 without writing it back (its contents are dead)
+__device__ __forceinline__ void l2_discard_128(const void* ptr)
+{
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(ptr) : "memory");
+}
+
 // log2 on the MUFU unit, flush-to-zero form: no denormal pre-scaling instructions.  Inputs
 // here are sums of squares of integers (exact zero or >= 1), never denormal.  lg2(0) = -inf.
 __device__ __forceinline__ float lg2_ftz(float x)

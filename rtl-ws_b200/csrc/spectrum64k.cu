@@ -173,6 +173,12 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
             }
             if (j == K - 1 && tid == 1023 % S64_THREADS) *dc_slot = dcacc;
             __syncthreads();          // frame32 / Z are rewritten by the next frame; dc_slot is visible
+            // Z(frame) is dead now.  Its 4096 dirty L2 lines would otherwise be written back to HBM before the
+            // next frame overwrites them (the reuse distance across 148 CTAs is ~200 MB, more than the L2 holds:
+            // ncu showed 6 of the 8 GB of scratch writes per 524 M samples going to DRAM): drop them instead.
+#pragma unroll 4
+            for (int i = tid; i < N64K * 8 / 128; i += S64_THREADS)
+                l2_discard_128(reinterpret_cast<const char*>(Z) + 128 * (size_t) i);
         }
 
         // spectrum.c:30-33: the DC position takes the (cumulative) value of its left neighbour, bin N-1
