@@ -201,6 +201,35 @@ def run_ref_bench(n_streams: int, samples_per_stream: int, workers: int, mode: s
     return json.loads(res.stdout.strip().splitlines()[-1])
 
 
+def fft_brackets():
+    """the CPU figure's FFT is the f64 stand-in, not FFTW (absent).  Two library f64 FFTs on the
+    same host, one thread each, 1024-point frames, as sanity brackets for it (Msamples/s, FFT only)."""
+    out = {}
+    n_frames = 16384
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((n_frames, 1024)) + 1j * rng.standard_normal((n_frames, 1024))
+    try:
+        np.fft.fft(x[:256], axis=1)
+        t0 = time.perf_counter()
+        np.fft.fft(x, axis=1)
+        out["numpy_pocketfft_f64_1thread_msamples_per_s"] = n_frames * 1024 / (time.perf_counter() - t0) / 1e6
+    except Exception:
+        pass
+    try:
+        import torch
+        old = torch.get_num_threads()
+        torch.set_num_threads(1)
+        xt = torch.from_numpy(x)
+        torch.fft.fft(xt[:256], dim=1)
+        t0 = time.perf_counter()
+        torch.fft.fft(xt, dim=1)
+        out["torch_f64_1thread_msamples_per_s"] = n_frames * 1024 / (time.perf_counter() - t0) / 1e6
+        torch.set_num_threads(old)
+    except Exception:
+        pass
+    return out
+
+
 def cpu_sample_shape(cpu_seconds: float, workers: int):
     """A bounded sample of the workload: whole streams of 1 s (2 048 000 samples), enough of them for
     ~cpu_seconds of CPU work per worker at ~20 Msamples/s/core."""
@@ -447,6 +476,7 @@ def main():
             r1 = run_ref_bench(max(1, n_s // workers), per, 1)
             if r1 is not None:
                 cpu_baseline["value_1core"] = r1["msamples_per_s"]
+            cpu_baseline["fft_only_brackets"] = fft_brackets()
 
     if rank == 0:
         line = {
