@@ -143,36 +143,46 @@ __global__ void __launch_bounds__(FM_THREADS) fm_chain_kernel(const FmParams p, 
     }
 }
 
-// ---- R = 10 (the reference's default, cbb_main.c:80): one WARP per tile, no block barriers ----
+// ---- 3 <= R <= 16 (R = 10 is the reference's default, cbb_main.c:80; its `bw` command gives
+//      R = fs / 192000, main.c:154: 5 at 1.024, 12 at 2.4, 13 at 2.56, 15 at 2.88, 16 at 3.2 MS/s):
+//      one WARP per tile, no block barriers ----
 // Tile = 62 audio samples: 4*62 + 31 = 279 = 9 * 31 demodulator outputs, i.e. exactly nine
-// shuffle chunks (lane 0 of a chunk only supplies the previous phase).  Input = 2480 + 320
-// samples = 5600 bytes per TMA copy, two-deep warp-private ring; 13 KB of shared memory per
-// warp, 16 warps per SM.  Straight-line code: chunks that run past a short last tile read
-// stale bytes of the ring and their results are simply not stored.
-constexpr int F10_T = 62;
-constexpr int F10_ND = 4 * F10_T + 32;            // 280 decimated samples, local index 0 <-> 4*n0 - 32
-constexpr int F10_STAGE = F10_ND * 20;            // 5600 bytes
-constexpr int F10_NW = 2 * F10_T + 10;            // 134 first-stage outputs
-constexpr int F10_WARPS = 8;                      // per CTA: two per scheduler
-constexpr int F10_WARP_SMEM = 2 * F10_STAGE + 288 * 4 + 144 * 4 + 32;   // ring, demod[], work[], 2 mbarriers (+pad)
-static_assert(F10_WARP_SMEM % 16 == 0, "TMA destinations must stay 16-byte aligned");
+// shuffle chunks (lane 0 of a chunk only supplies the previous phase).  Input = (248 + 32) * R
+// samples per TMA copy (5600 bytes at R = 10), two-deep warp-private ring; 13 KB of shared memory
+// per warp at R = 10 (16 warps per SM).  Straight-line code: chunks that run past a short last tile
+// read stale bytes of the ring and their results are simply not stored.
+constexpr int FW_T = 62;
+constexpr int FW_ND = 4 * FW_T + 32;              // 280 decimated samples, local index 0 <-> 4*n0 - 32
+constexpr int FW_NW = 2 * FW_T + 10;              // 134 first-stage outputs
+constexpr int FW_WARPS = 8;                       // per CTA: two per scheduler
 
-__global__ void __launch_bounds__(F10_WARPS * 32, 2) fm_chain10_kernel(const FmParams p, const int tiles_per_stream)
+template <int R>
+struct FwCfg {
+    static constexpr int SAMPLE_BYTES = 2 * R;                     // one decimated sample's input
+    static constexpr int STAGE = FW_ND * SAMPLE_BYTES;            // 5600 bytes at R = 10
+    static constexpr int WARP_SMEM = 2 * STAGE + 288 * 4 + 144 * 4 + 32;   // ring, demod[], work[], 2 mbarriers (+pad)
+    static_assert(WARP_SMEM % 16 == 0, "TMA destinations must stay 16-byte aligned");
+    static constexpr int CTAS = (225 * 1024) / (FW_WARPS * WARP_SMEM + 1024) >= 2 ? 2 : 1;     // resident CTAs the compiler may plan for
+};
+
+template <int R>
+__global__ void __launch_bounds__(FW_WARPS * 32, FwCfg<R>::CTAS) fm_chain_warp_kernel(const FmParams p, const int tiles_per_stream)
 {
+    using C = FwCfg<R>;
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    uint8_t* wbase = smem + warp * F10_WARP_SMEM;
+    uint8_t* wbase = smem + warp * C::WARP_SMEM;
     uint8_t* ring = wbase;
-    float* demod = reinterpret_cast<float*>(wbase + 2 * F10_STAGE);
+    float* demod = reinterpret_cast<float*>(wbase + 2 * C::STAGE);
     float* work = demod + 288;
     uint64_t* bars = reinterpret_cast<uint64_t*>(work + 144);
 
-    const int64_t n_audio = p.n_samples / 40;
+    const int64_t n_audio = p.n_samples / (4 * R);
     const uint32_t tps = (uint32_t) tiles_per_stream;
     const uint32_t total_tiles = (uint32_t) p.n_streams * tps;
-    const uint32_t gw = blockIdx.x * F10_WARPS + warp;
-    const uint32_t GW = gridDim.x * F10_WARPS;
+    const uint32_t gw = blockIdx.x * FW_WARPS + warp;
+    const uint32_t GW = gridDim.x * FW_WARPS;
     if (gw >= total_tiles) return;
     const uint32_t n_mine = (total_tiles - gw + GW - 1) / GW;
 
@@ -186,13 +196,16 @@ __global__ void __launch_bounds__(F10_WARPS * 32, 2) fm_chain10_kernel(const FmP
     auto issue = [&](uint32_t it) {
         const uint32_t tile = gw + it * GW;
         const uint32_t s = tile / tps;
-        const int64_t n0 = (int64_t) (tile - s * tps) * F10_T;
-        const int ta = (int) ((n_audio - n0) < F10_T ? (n_audio - n0) : F10_T);
-        const uint32_t bytes = (uint32_t) (4 * ta + 32) * 20u;
-        const uint8_t* src = p.iq + (int64_t) s * p.stream_stride_bytes + (4 * n0 - 32) * 20;
+        const int64_t n0 = (int64_t) (tile - s * tps) * FW_T;
+        const int ta = (int) ((n_audio - n0) < FW_T ? (n_audio - n0) : FW_T);
+        // (4 ta + 32) * 2R = 8 (ta + 8) R bytes from byte 8 (n0 - 8) R of the batch.  Both are multiples of 16:
+        // n0 is a multiple of 62, and ta is even -- for odd R because n_samples = 4 R n_audio must be a multiple
+        // of 8 (launch_fm_chain checks it), so n_audio and every n_audio - 62 k are even; for even R regardless.
+        const uint32_t bytes = (uint32_t) (4 * ta + 32) * (uint32_t) C::SAMPLE_BYTES;
+        const uint8_t* src = p.iq + (int64_t) s * p.stream_stride_bytes + (4 * n0 - 32) * C::SAMPLE_BYTES;
         const int st = it & 1;
         mbar_arrive_expect_tx(&bars[st], bytes);
-        tma_load_1d(ring + st * F10_STAGE, src, bytes, &bars[st]);
+        tma_load_1d(ring + st * C::STAGE, src, bytes, &bars[st]);
     };
     if (lane == 0) {
         issue(0);
@@ -203,10 +216,10 @@ __global__ void __launch_bounds__(F10_WARPS * 32, 2) fm_chain10_kernel(const FmP
         const int st = it & 1;
         const uint32_t tile = gw + it * GW;
         const uint32_t s = tile / tps;
-        const int64_t n0 = (int64_t) (tile - s * tps) * F10_T;
-        const int ta = (int) ((n_audio - n0) < F10_T ? (n_audio - n0) : F10_T);
+        const int64_t n0 = (int64_t) (tile - s * tps) * FW_T;
+        const int ta = (int) ((n_audio - n0) < FW_T ? (n_audio - n0) : FW_T);
         mbar_wait(&bars[st], (it >> 1) & 1);
-        const uint8_t* in = ring + st * F10_STAGE;
+        const uint8_t* in = ring + st * C::STAGE;
 
         // ---- discriminator: 9 chunks of 31 outputs (resample.c:21-40, common_sp.h:40-76,
         //      audio_main.c:110-131) ----
@@ -214,7 +227,10 @@ __global__ void __launch_bounds__(F10_WARPS * 32, 2) fm_chain10_kernel(const FmP
         for (int c = 0; c < 9; ++c) {
             const int j = 31 * c + lane;
             uint32_t ure, uim;
-            cic10_sum(reinterpret_cast<const uint32_t*>(in + j * 20), ure, uim);
+            if constexpr (R % 2 == 0)
+                cic_even_sum<R>(reinterpret_cast<const uint32_t*>(in + j * C::SAMPLE_BYTES), ure, uim);
+            else
+                cic_odd_sum<R>(reinterpret_cast<const uint16_t*>(in + j * C::SAMPLE_BYTES), ure, uim);
             const float ph = atan2_approx_dev(__uint_as_float(uim) - CIC_MAGIC, __uint_as_float(ure) - CIC_MAGIC);
             const float prev = __shfl_up_sync(0xffffffffu, ph, 1);
             if (lane > 0) demod[j] = fm_limit(ph, prev);
@@ -232,7 +248,7 @@ __global__ void __launch_bounds__(F10_WARPS * 32, 2) fm_chain10_kernel(const FmP
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
             const int m = 32 * r + lane;
-            if (m < F10_NW) work[m] = halfband_from(demod + 2 * m + 2);
+            if (m < FW_NW) work[m] = halfband_from(demod + 2 * m + 2);
         }
         __syncwarp();
         // ---- half-band #2 (audio_main.c:139) ----
@@ -244,6 +260,28 @@ __global__ void __launch_bounds__(F10_WARPS * 32, 2) fm_chain10_kernel(const FmP
         }
         __syncwarp();       // demod[] / work[] are rewritten by the next tile
     }
+}
+
+template <int R>
+int launch_fm_warp(const FmParams& p, cudaStream_t stream)
+{
+    using C = FwCfg<R>;
+    const int64_t n_audio = p.n_samples / (4 * R);
+    const int64_t tps = (n_audio + FW_T - 1) / FW_T;
+    const int64_t total = (int64_t) p.n_streams * tps;
+    if (total >= (1ll << 31)) {
+        set_error("fm: batch too long");
+        return B200_ERR_ARG;
+    }
+    const int smem = FW_WARPS * C::WARP_SMEM;
+    if (int rc = ensure_dynamic_smem((const void*) fm_chain_warp_kernel<R>, smem)) return rc;
+    const int per_sm = cached_occupancy((const void*) fm_chain_warp_kernel<R>, FW_WARPS * 32, smem);
+    int64_t grid = (int64_t) sm_count() * per_sm;
+    const int64_t needed = (total + FW_WARPS - 1) / FW_WARPS;
+    if (grid > needed) grid = needed;
+    fm_chain_warp_kernel<R><<<(unsigned) grid, FW_WARPS * 32, smem, stream>>>(p, (int) tps);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
 }
 
 // history <- last H samples of the batch (per stream); H*2 bytes, 16-byte granules
@@ -294,23 +332,22 @@ int launch_fm_chain(const FmParams& p, cudaStream_t stream)
         return B200_ERR_ALIGN;
     }
     if (p.n_streams == 0 || p.n_samples == 0) return B200_OK;
-    if (p.R == 10) {
-        const int64_t n_audio10 = p.n_samples / 40;
-        const int64_t tps = (n_audio10 + F10_T - 1) / F10_T;
-        const int64_t total = (int64_t) p.n_streams * tps;
-        if (total >= (1ll << 31)) {
-            set_error("fm: batch too long");
-            return B200_ERR_ARG;
-        }
-        const int smem10 = F10_WARPS * F10_WARP_SMEM;
-        if (int rc = ensure_dynamic_smem((const void*) fm_chain10_kernel, smem10)) return rc;
-        const int per_sm = cached_occupancy((const void*) fm_chain10_kernel, F10_WARPS * 32, smem10);
-        int64_t grid10 = (int64_t) sm_count() * per_sm;
-        const int64_t needed = (total + F10_WARPS - 1) / F10_WARPS;
-        if (grid10 > needed) grid10 = needed;
-        fm_chain10_kernel<<<(unsigned) grid10, F10_WARPS * 32, smem10, stream>>>(p, (int) tps);
-        B200_LAUNCH_CHECK();
-        return B200_OK;
+    switch (p.R) {                                  // small down factors: the warp-per-tile kernel
+        case 3: return launch_fm_warp<3>(p, stream);
+        case 5: return launch_fm_warp<5>(p, stream);
+        case 7: return launch_fm_warp<7>(p, stream);
+        case 9: return launch_fm_warp<9>(p, stream);
+        case 11: return launch_fm_warp<11>(p, stream);
+        case 13: return launch_fm_warp<13>(p, stream);
+        case 15: return launch_fm_warp<15>(p, stream);
+        case 4: return launch_fm_warp<4>(p, stream);
+        case 6: return launch_fm_warp<6>(p, stream);
+        case 8: return launch_fm_warp<8>(p, stream);
+        case 10: return launch_fm_warp<10>(p, stream);
+        case 12: return launch_fm_warp<12>(p, stream);
+        case 14: return launch_fm_warp<14>(p, stream);
+        case 16: return launch_fm_warp<16>(p, stream);
+        default: break;
     }
     const int T = fm_tile_audio(p.R);
     const int64_t n_audio = p.n_samples / (4 * p.R);

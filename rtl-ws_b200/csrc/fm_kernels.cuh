@@ -33,6 +33,35 @@ __device__ __forceinline__ void cic10_sum(const uint32_t* w, uint32_t& ure, uint
     }
 }
 
+// even R: R/2 aligned 32-bit words (a decimated sample starts on a word boundary when 2R is a multiple of 4)
+template <int R>
+__device__ __forceinline__ void cic_even_sum(const uint32_t* w, uint32_t& ure, uint32_t& uim)
+{
+    static_assert(R % 2 == 0, "word-wise CIC sum needs an even down factor");
+    ure = CIC_MAGIC_BITS - 128u * (uint32_t) R;
+    uim = CIC_MAGIC_BITS - 128u * (uint32_t) R;
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) {
+        const uint32_t v = w[k];
+        ure = __dp4a(v, 0x00010001u, ure);
+        uim = __dp4a(v, 0x01000100u, uim);
+    }
+}
+
+// odd R: R aligned 16-bit loads (a decimated sample starts on a 2-byte boundary only)
+template <int R>
+__device__ __forceinline__ void cic_odd_sum(const uint16_t* h, uint32_t& ure, uint32_t& uim)
+{
+    ure = CIC_MAGIC_BITS - 128u * (uint32_t) R;
+    uim = CIC_MAGIC_BITS - 128u * (uint32_t) R;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const uint32_t v = h[k];
+        ure += v & 0xffu;
+        uim += v >> 8;
+    }
+}
+
 // any R, sample-wise
 __device__ __forceinline__ void cic_sum(const uint16_t* h, int R, uint32_t& ure, uint32_t& uim)
 {

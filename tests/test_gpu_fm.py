@@ -23,7 +23,7 @@ def oracle_stream(po, iq, R=10):
     return dec, audio
 
 
-@pytest.mark.parametrize("R", [10, 5, 12, 16, 1, 7, 64])
+@pytest.mark.parametrize("R", [10, 5, 12, 16, 1, 7, 64, 3, 4, 6, 8, 9, 11, 13, 14, 15, 2, 17])
 def test_fm_exec_matches_oracle(pkg, cuda, po, synth, R):
     torch = cuda
     n = 4 * R * 8 * 61              # whole audio samples, multiple of 8, not a multiple of the tile
