@@ -133,6 +133,14 @@ int b200_fm_exec(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams
 int b200_chain_exec(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams, int64_t n_samples,
                     int gain_db, float* d_db, float* d_audio, int64_t audio_stride,
                     uint8_t* d_avg_u8, int K_avg, void* cuda_stream);
+/* The same for any down factor R in [1, 256] (the reference's `bw` command re-derives it as fs / 192000,
+ * main.c:152-155, cbb_main.c:80): n_samples must be a multiple of b200_chain_tile_samples(R) = lcm(1024, 4R),
+ * history is b200_fm_history_samples(R) samples, d_audio holds n_samples / (4R) floats per stream.  R = 10
+ * runs the fused one-pass kernel; other factors run the spectrum and the FM kernel over the same bytes. */
+int64_t b200_chain_tile_samples(int R);
+int b200_chain_exec_r(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams, int64_t n_samples, int R,
+                      int gain_db, float* d_db, float* d_audio, int64_t audio_stride,
+                      uint8_t* d_avg_u8, int K_avg, void* cuda_stream);
 
 /* ---- host-buffer entry point (what a plugin calls; includes the PCIe copies) --------------
  *
@@ -144,6 +152,8 @@ int b200_chain_exec(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_stre
  */
 typedef struct b200_session b200_session;
 b200_session* b200_session_create(int n_streams, int64_t max_samples_per_batch);
+/* any down factor (b200_session_create is R = 10); batches are multiples of b200_chain_tile_samples(R) */
+b200_session* b200_session_create_r(int n_streams, int64_t max_samples_per_batch, int R);
 void b200_session_destroy(b200_session* s);
 void b200_session_reset(b200_session* s);      /* all streams back to stream start */
 int b200_session_chain(b200_session* s, const uint8_t* h_iq, int64_t n_samples, int gain_db,
@@ -166,6 +176,9 @@ typedef struct b200_stream b200_stream;
 typedef void (*b200_spectrum_sink)(void* user, int stream, int64_t first_frame, int n_frames, const float* db);
 typedef void (*b200_audio_sink)(void* user, int stream, int64_t first_sample, int n, const float* audio);
 b200_stream* b200_stream_create(int n_streams, int64_t batch_samples, int gain_db);
+/* any down factor (b200_stream_create is R = 10): batch_samples a multiple of b200_chain_tile_samples(R),
+ * the audio sink gets batch_samples / (4R) floats per batch at fs / (4R) */
+b200_stream* b200_stream_create_r(int n_streams, int64_t batch_samples, int gain_db, int R);
 void b200_stream_destroy(b200_stream* s);
 void b200_stream_set_sinks(b200_stream* s, b200_spectrum_sink spectrum_sink, b200_audio_sink audio_sink, void* user);
 /* samples: len interleaved (re, im) byte pairs, i.e. a `const cmplx_u8*` */

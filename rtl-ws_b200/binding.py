@@ -26,9 +26,9 @@ EXPORTED_SYMBOLS = [
     "b200_spectrum_plan_create", "b200_spectrum_plan_destroy", "b200_spectrum_plan_rows", "b200_spectrum_exec",
     "b200_spectrum_exec_cs32", "b200_spectrum_exec_rf32",
     "b200_fm_history_samples", "b200_fm_history_reset", "b200_fm_history_carry", "b200_fm_exec",
-    "b200_chain_exec",
-    "b200_session_create", "b200_session_destroy", "b200_session_reset", "b200_session_chain",
-    "b200_stream_create", "b200_stream_destroy", "b200_stream_set_sinks", "b200_stream_push", "b200_stream_poll",
+    "b200_chain_exec", "b200_chain_exec_r", "b200_chain_tile_samples",
+    "b200_session_create", "b200_session_create_r", "b200_session_destroy", "b200_session_reset", "b200_session_chain",
+    "b200_stream_create", "b200_stream_create_r", "b200_stream_destroy", "b200_stream_set_sinks", "b200_stream_push", "b200_stream_poll",
     "b200_stream_flush", "b200_stream_pending_samples",
     "b200_wire_spectrum_header", "b200_wire_spectrum_message", "b200_wire_spectrum_messages",
     "b200_wire_audio_messages", "b200_wire_audio_fragment", "b200_wire_reference_drain_index",
@@ -86,8 +86,15 @@ def lib() -> C.CDLL:
     L.b200_fm_history_carry.argtypes = [vp, i64, i32, i64, i32, vp]
     L.b200_fm_exec.argtypes = [vp, i64, i32, i64, i32, f32p, i64, vp, i64, vp]
     L.b200_chain_exec.argtypes = [vp, i64, i32, i64, i32, f32p, f32p, i64, vp, i32, vp]
+    L.b200_chain_exec_r.argtypes = [vp, i64, i32, i64, i32, i32, f32p, f32p, i64, vp, i32, vp]
+    L.b200_chain_tile_samples.restype = i64
+    L.b200_chain_tile_samples.argtypes = [i32]
     L.b200_session_create.restype = vp
     L.b200_session_create.argtypes = [i32, i64]
+    L.b200_session_create_r.restype = vp
+    L.b200_session_create_r.argtypes = [i32, i64, i32]
+    L.b200_stream_create_r.restype = vp
+    L.b200_stream_create_r.argtypes = [i32, i64, i32, i32]
     L.b200_session_destroy.argtypes = [vp]
     L.b200_session_reset.argtypes = [vp]
     L.b200_session_chain.argtypes = [vp, vp, i64, i32, vp, vp]
@@ -295,28 +302,27 @@ def fm_exec(ring: StreamRing, audio=None, decimated: bool = False, stream=None):
 def chain_exec(ring: StreamRing, gain_db: int = 0, db=None, audio=None, avg_u8=None, K_avg: int = 6, stream=None):
     """b200_chain_exec: per-frame dB spectra (N = 1024) + FM audio from one pass over the ring's batch."""
     torch = _torch()
-    assert ring.R == 10
-    n_audio = ring.n_samples // 40
+    n_audio = ring.n_samples // (4 * ring.R)
     if db is None:
         db = torch.empty((ring.n_streams, ring.n_samples // 1024, 1024), dtype=torch.float32, device=ring.buf.device)
     if audio is None:
         audio = torch.empty((ring.n_streams, n_audio), dtype=torch.float32, device=ring.buf.device)
-    _check(lib().b200_chain_exec(C.c_void_p(ring.batch.data_ptr()), ring.stride_bytes, ring.n_streams,
-                                 ring.n_samples, gain_db, C.c_void_p(db.data_ptr()), C.c_void_p(audio.data_ptr()),
-                                 audio.stride(0), C.c_void_p(avg_u8.data_ptr()) if avg_u8 is not None else None,
-                                 K_avg, _stream_ptr(stream)), "b200_chain_exec")
+    _check(lib().b200_chain_exec_r(C.c_void_p(ring.batch.data_ptr()), ring.stride_bytes, ring.n_streams,
+                                   ring.n_samples, ring.R, gain_db, C.c_void_p(db.data_ptr()), C.c_void_p(audio.data_ptr()),
+                                   audio.stride(0), C.c_void_p(avg_u8.data_ptr()) if avg_u8 is not None else None,
+                                   K_avg, _stream_ptr(stream)), "b200_chain_exec_r")
     return db, audio
 
 
 class Session:
     """b200_session_*: the host-buffer entry point (PCIe copies inside)."""
 
-    def __init__(self, n_streams: int, max_samples: int):
+    def __init__(self, n_streams: int, max_samples: int, R: int = 10):
         _torch()
-        self.n_streams, self.max_samples = n_streams, max_samples
-        self.h = lib().b200_session_create(n_streams, max_samples)
+        self.n_streams, self.max_samples, self.R = n_streams, max_samples, R
+        self.h = lib().b200_session_create_r(n_streams, max_samples, R)
         if not self.h:
-            raise B200Error(f"b200_session_create: {last_error()}")
+            raise B200Error(f"b200_session_create_r: {last_error()}")
 
     def close(self):
         if getattr(self, "h", None):
@@ -345,12 +351,12 @@ class Session:
 class PushStream:
     """b200_stream_*: signal_source-style pushes in, spectra and audio out through sinks."""
 
-    def __init__(self, n_streams: int, batch_samples: int, gain_db: int = 0):
+    def __init__(self, n_streams: int, batch_samples: int, gain_db: int = 0, R: int = 10):
         _torch()
-        self.n_streams, self.batch = n_streams, batch_samples
-        self.h = lib().b200_stream_create(n_streams, batch_samples, gain_db)
+        self.n_streams, self.batch, self.R = n_streams, batch_samples, R
+        self.h = lib().b200_stream_create_r(n_streams, batch_samples, gain_db, R)
         if not self.h:
-            raise B200Error(f"b200_stream_create: {last_error()}")
+            raise B200Error(f"b200_stream_create_r: {last_error()}")
         self.spectra = [[] for _ in range(n_streams)]      # (first_frame, [n_frames, 1024] copy)
         self.audio = [[] for _ in range(n_streams)]        # (first_sample, [n] copy)
 

@@ -23,6 +23,16 @@ constexpr int CHAIN_N = 1024;      // cbb_main.c:17 FFT_POINTS
 constexpr int CHAIN_R = 10;        // cbb_main.c:80 at rtl_sensor.c:12's 2.048 MS/s and main.c:23's 192 kHz
 constexpr int CHAIN_TILE = 5120;   // lcm(1024, 4 * R): 5 frames = 128 audio samples
 
+int64_t gcd64(int64_t a, int64_t b)
+{
+    while (b) {
+        const int64_t t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
 std::mutex g_plan_mutex;
 // (device, K, gain_db) -> plan; plans are tiny (a twiddle table) and live for the process
 std::map<std::tuple<int, int, int>, b200_spectrum_plan*> g_plans;
@@ -48,12 +58,32 @@ extern "C" float b200_spectrum_plan_db_offset_(const b200_spectrum_plan* plan);
 
 extern "C" {
 
+int64_t b200_chain_tile_samples(int R)
+{
+    if (R < 1 || R > 256) return B200_ERR_ARG;
+    const int64_t a = CHAIN_N, b = 4 * (int64_t) R;
+    return a / gcd64(a, b) * b;                 // lcm(1024, 4R): whole frames and whole audio samples (a multiple of 8)
+}
+
 int b200_chain_exec(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams, int64_t n_samples, int gain_db,
                     float* d_db, float* d_audio, int64_t audio_stride, uint8_t* d_avg_u8, int K_avg,
                     void* cuda_stream)
 {
-    if (d_iq == nullptr || n_streams < 0 || n_samples < 0 || n_samples % CHAIN_TILE != 0) {
-        set_error("chain exec: n_samples %lld must be a non-negative multiple of %d", (long long) n_samples, CHAIN_TILE);
+    return b200_chain_exec_r(d_iq, stream_stride_bytes, n_streams, n_samples, CHAIN_R, gain_db, d_db, d_audio,
+                             audio_stride, d_avg_u8, K_avg, cuda_stream);
+}
+
+int b200_chain_exec_r(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams, int64_t n_samples, int R,
+                      int gain_db, float* d_db, float* d_audio, int64_t audio_stride, uint8_t* d_avg_u8, int K_avg,
+                      void* cuda_stream)
+{
+    const int64_t tile = b200_chain_tile_samples(R);
+    if (tile < 0) {
+        set_error("chain exec: down factor %d outside [1, 256]", R);
+        return B200_ERR_ARG;
+    }
+    if (d_iq == nullptr || n_streams < 0 || n_samples < 0 || n_samples % tile != 0) {
+        set_error("chain exec: n_samples %lld must be a non-negative multiple of %lld", (long long) n_samples, (long long) tile);
         return B200_ERR_ARG;
     }
     if ((reinterpret_cast<uintptr_t>(d_iq) & 15) != 0 || (stream_stride_bytes & 15) != 0) {
@@ -66,7 +96,7 @@ int b200_chain_exec(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_stre
     if (pl == nullptr) return B200_ERR_CUDA;
 
     int rc;
-    if (d_db != nullptr && d_audio != nullptr) {
+    if (d_db != nullptr && d_audio != nullptr && R == CHAIN_R) {      // one pass over the IQ (chain_fused.cu)
         rc = launch_chain_fused(d_iq, stream_stride_bytes, n_streams, n_samples, b200_spectrum_plan_db_offset_(pl),
                                 reinterpret_cast<const float2*>(b200_spectrum_plan_twiddle_(pl)), d_db, d_audio,
                                 audio_stride, stream);
@@ -78,7 +108,7 @@ int b200_chain_exec(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_stre
             if (rc) return rc;
         }
         if (d_audio != nullptr) {
-            rc = b200_fm_exec(d_iq, stream_stride_bytes, n_streams, n_samples, CHAIN_R, d_audio, audio_stride, nullptr,
+            rc = b200_fm_exec(d_iq, stream_stride_bytes, n_streams, n_samples, R, d_audio, audio_stride, nullptr,
                               0, cuda_stream);
             if (rc) return rc;
         }
@@ -103,11 +133,13 @@ int b200_chain_exec(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_stre
 struct b200_session {
     int n_streams;
     int64_t max_samples;
+    int R;                     // down factor of the FM branch
+    int64_t tile;              // lcm(1024, 4R)
     int hist_samples;
     int64_t stride_bytes;      // per-stream row pitch in the device ring: history + batch
     uint8_t* d_ring;           // [n_streams][stride_bytes]
     float* d_db;               // [n_streams][max_samples]            (1024 bins per 1024 samples)
-    float* d_audio;            // [n_streams][max_samples / 40]
+    float* d_audio;            // [n_streams][max_samples / (4R)]
     static constexpr int LANES = 4;
     cudaStream_t streams[LANES];
     int device;
@@ -117,20 +149,32 @@ extern "C" {
 
 b200_session* b200_session_create(int n_streams, int64_t max_samples_per_batch)
 {
-    if (n_streams < 1 || max_samples_per_batch < CHAIN_TILE || max_samples_per_batch % CHAIN_TILE != 0) {
-        set_error("session: max_samples_per_batch must be a positive multiple of %d", CHAIN_TILE);
+    return b200_session_create_r(n_streams, max_samples_per_batch, CHAIN_R);
+}
+
+b200_session* b200_session_create_r(int n_streams, int64_t max_samples_per_batch, int R)
+{
+    const int64_t tile = b200_chain_tile_samples(R);
+    if (tile < 0) {
+        set_error("session: down factor %d outside [1, 256]", R);
+        return nullptr;
+    }
+    if (n_streams < 1 || max_samples_per_batch < tile || max_samples_per_batch % tile != 0) {
+        set_error("session: max_samples_per_batch must be a positive multiple of %lld", (long long) tile);
         return nullptr;
     }
     b200_session* s = new b200_session();
     memset(s, 0, sizeof(*s));
     s->n_streams = n_streams;
     s->max_samples = max_samples_per_batch;
-    s->hist_samples = fm_history_samples(CHAIN_R);
+    s->R = R;
+    s->tile = tile;
+    s->hist_samples = fm_history_samples(R);
     s->stride_bytes = 2 * ((int64_t) s->hist_samples + max_samples_per_batch);
     bool ok = cudaGetDevice(&s->device) == cudaSuccess;
     ok = ok && cudaMalloc(&s->d_ring, (size_t) n_streams * (size_t) s->stride_bytes) == cudaSuccess;
     ok = ok && cudaMalloc(&s->d_db, sizeof(float) * (size_t) n_streams * (size_t) max_samples_per_batch) == cudaSuccess;
-    ok = ok && cudaMalloc(&s->d_audio, sizeof(float) * (size_t) n_streams * (size_t) (max_samples_per_batch / 40)) ==
+    ok = ok && cudaMalloc(&s->d_audio, sizeof(float) * (size_t) n_streams * (size_t) (max_samples_per_batch / (4 * R))) ==
                    cudaSuccess;
     for (int i = 0; ok && i < b200_session::LANES; ++i)
         ok = cudaStreamCreateWithFlags(&s->streams[i], cudaStreamNonBlocking) == cudaSuccess;
@@ -157,7 +201,7 @@ void b200_session_destroy(b200_session* s)
 void b200_session_reset(b200_session* s)
 {
     if (s == nullptr) return;
-    launch_fm_history_reset(s->d_ring + 2 * (int64_t) s->hist_samples, s->stride_bytes, s->n_streams, CHAIN_R,
+    launch_fm_history_reset(s->d_ring + 2 * (int64_t) s->hist_samples, s->stride_bytes, s->n_streams, s->R,
                             s->streams[0]);
     cudaStreamSynchronize(s->streams[0]);
 }
@@ -165,9 +209,9 @@ void b200_session_reset(b200_session* s)
 int b200_session_chain(b200_session* s, const uint8_t* h_iq, int64_t n_samples, int gain_db, float* h_db,
                        float* h_audio)
 {
-    if (s == nullptr || h_iq == nullptr || n_samples < 0 || n_samples > s->max_samples || n_samples % CHAIN_TILE != 0) {
-        set_error("session chain: n_samples %lld must be a multiple of %d and at most %lld", (long long) n_samples,
-                  CHAIN_TILE, s ? (long long) s->max_samples : 0ll);
+    if (s == nullptr || h_iq == nullptr || n_samples < 0 || n_samples > s->max_samples || n_samples % s->tile != 0) {
+        set_error("session chain: n_samples %lld must be a multiple of %lld and at most %lld", (long long) n_samples,
+                  s ? (long long) s->tile : 0ll, s ? (long long) s->max_samples : 0ll);
         return B200_ERR_ARG;
     }
     if (n_samples == 0) return B200_OK;
@@ -175,7 +219,7 @@ int b200_session_chain(b200_session* s, const uint8_t* h_iq, int64_t n_samples, 
     // stream groups small enough to pipeline H2D / kernels / D2H across the lanes
     int group = (s->n_streams + 4 * lanes - 1) / (4 * lanes);
     if (group < 1) group = 1;
-    const int64_t n_audio = n_samples / 40;
+    const int64_t n_audio = n_samples / (4 * s->R);
     int lane = 0;
     for (int s0 = 0; s0 < s->n_streams; s0 += group, lane = (lane + 1) % lanes) {
         const int ns = (s->n_streams - s0) < group ? (s->n_streams - s0) : group;
@@ -186,8 +230,8 @@ int b200_session_chain(b200_session* s, const uint8_t* h_iq, int64_t n_samples, 
         B200_CUDA_TRY(cudaMemcpy2DAsync(d_batch, (size_t) s->stride_bytes, h_iq + (size_t) s0 * 2 * (size_t) n_samples,
                                         (size_t) (2 * n_samples), (size_t) (2 * n_samples), (size_t) ns,
                                         cudaMemcpyHostToDevice, st));
-        const int rc = b200_chain_exec(d_batch, s->stride_bytes, ns, n_samples, gain_db, h_db ? d_db : nullptr,
-                                       h_audio ? d_audio : nullptr, n_audio, nullptr, 0, st);
+        const int rc = b200_chain_exec_r(d_batch, s->stride_bytes, ns, n_samples, s->R, gain_db, h_db ? d_db : nullptr,
+                                         h_audio ? d_audio : nullptr, n_audio, nullptr, 0, st);
         if (rc) return rc;
         if (h_db)
             B200_CUDA_TRY(cudaMemcpyAsync(h_db + (size_t) s0 * (size_t) n_samples, d_db,
@@ -195,7 +239,7 @@ int b200_session_chain(b200_session* s, const uint8_t* h_iq, int64_t n_samples, 
         if (h_audio)
             B200_CUDA_TRY(cudaMemcpyAsync(h_audio + (size_t) s0 * (size_t) n_audio, d_audio,
                                           sizeof(float) * (size_t) ns * (size_t) n_audio, cudaMemcpyDeviceToHost, st));
-        const int rc2 = launch_fm_history_carry(d_batch, s->stride_bytes, ns, n_samples, CHAIN_R, st);
+        const int rc2 = launch_fm_history_carry(d_batch, s->stride_bytes, ns, n_samples, s->R, st);
         if (rc2) return rc2;
     }
     for (int i = 0; i < lanes; ++i) B200_CUDA_TRY(cudaStreamSynchronize(s->streams[i]));

@@ -26,7 +26,6 @@ int fm_history_samples(int R);
 }  // namespace b200
 
 namespace {
-constexpr int ST_TILE = 5120;
 constexpr int ST_R = 10;
 constexpr int ST_SLOTS = 2;
 constexpr int ST_LANES = 4;
@@ -36,14 +35,15 @@ struct b200_stream {
     int n_streams;
     int64_t batch;                 // samples per batch (multiple of 5120)
     int gain_db;
+    int R;                         // down factor of the FM branch
     int hist;                      // samples
     int64_t row_bytes;             // device row pitch: history + batch
     uint8_t* d_rows;               // [n_streams][ST_SLOTS? no: one row per stream][row_bytes]
     float* d_db;                   // [n_streams][batch]
-    float* d_audio;                // [n_streams][batch / 40]
+    float* d_audio;                // [n_streams][batch / (4R)]
     uint8_t* h_in;                 // pinned [n_streams][ST_SLOTS][2 * batch]
     float* h_db;                   // pinned [n_streams][ST_SLOTS][batch]
-    float* h_audio;                // pinned [n_streams][ST_SLOTS][batch / 40]
+    float* h_audio;                // pinned [n_streams][ST_SLOTS][batch / (4R)]
     cudaStream_t lanes[ST_LANES];
     struct PerStream {
         int64_t fill;              // samples in the current slot
@@ -75,7 +75,7 @@ static void stream_deliver(b200_stream* s, int i, bool block)
         if (s->spectrum_sink)
             s->spectrum_sink(s->user, i, b * (s->batch / 1024), (int) (s->batch / 1024), s->h_db + off * (size_t) s->batch);
         if (s->audio_sink)
-            s->audio_sink(s->user, i, b * (s->batch / 40), (int) (s->batch / 40), s->h_audio + off * (size_t) (s->batch / 40));
+            s->audio_sink(s->user, i, b * (s->batch / (4 * s->R)), (int) (s->batch / (4 * s->R)), s->h_audio + off * (size_t) (s->batch / (4 * s->R)));
         p.in_flight[slot] = false;
         ++p.batches_delivered;
     }
@@ -89,17 +89,17 @@ static int stream_submit(b200_stream* s, int i)
     cudaStream_t lane = s->lanes[i % ST_LANES];
     uint8_t* d_batch = s->d_rows + (size_t) i * (size_t) s->row_bytes + 2 * (size_t) s->hist;
     float* d_db = s->d_db + (size_t) i * (size_t) s->batch;
-    float* d_audio = s->d_audio + (size_t) i * (size_t) (s->batch / 40);
+    float* d_audio = s->d_audio + (size_t) i * (size_t) (s->batch / (4 * s->R));
     B200_CUDA_TRY(cudaMemcpyAsync(d_batch, s->h_in + off * 2 * (size_t) s->batch, 2 * (size_t) s->batch,
                                   cudaMemcpyHostToDevice, lane));
-    int rc = b200_chain_exec(d_batch, s->row_bytes, 1, s->batch, s->gain_db, d_db, d_audio, s->batch / 40, nullptr, 0, lane);
+    int rc = b200_chain_exec_r(d_batch, s->row_bytes, 1, s->batch, s->R, s->gain_db, d_db, d_audio, s->batch / (4 * s->R), nullptr, 0, lane);
     if (rc) return rc;
-    rc = launch_fm_history_carry(d_batch, s->row_bytes, 1, s->batch, ST_R, lane);
+    rc = launch_fm_history_carry(d_batch, s->row_bytes, 1, s->batch, s->R, lane);
     if (rc) return rc;
     B200_CUDA_TRY(cudaMemcpyAsync(s->h_db + off * (size_t) s->batch, d_db, sizeof(float) * (size_t) s->batch,
                                   cudaMemcpyDeviceToHost, lane));
-    B200_CUDA_TRY(cudaMemcpyAsync(s->h_audio + off * (size_t) (s->batch / 40), d_audio,
-                                  sizeof(float) * (size_t) (s->batch / 40), cudaMemcpyDeviceToHost, lane));
+    B200_CUDA_TRY(cudaMemcpyAsync(s->h_audio + off * (size_t) (s->batch / (4 * s->R)), d_audio,
+                                  sizeof(float) * (size_t) (s->batch / (4 * s->R)), cudaMemcpyDeviceToHost, lane));
     B200_CUDA_TRY(cudaEventRecord(p.done[slot], lane));
     p.in_flight[slot] = true;
     ++p.batches_submitted;
@@ -112,15 +112,26 @@ extern "C" {
 
 b200_stream* b200_stream_create(int n_streams, int64_t batch_samples, int gain_db)
 {
-    if (n_streams < 1 || batch_samples < ST_TILE || batch_samples % ST_TILE != 0) {
-        set_error("stream: batch_samples must be a positive multiple of %d", ST_TILE);
+    return b200_stream_create_r(n_streams, batch_samples, gain_db, ST_R);
+}
+
+b200_stream* b200_stream_create_r(int n_streams, int64_t batch_samples, int gain_db, int R)
+{
+    const int64_t tile = b200_chain_tile_samples(R);
+    if (tile < 0) {
+        set_error("stream: down factor %d outside [1, 256]", R);
+        return nullptr;
+    }
+    if (n_streams < 1 || batch_samples < tile || batch_samples % tile != 0) {
+        set_error("stream: batch_samples must be a positive multiple of %lld", (long long) tile);
         return nullptr;
     }
     b200_stream* s = new b200_stream();
     s->n_streams = n_streams;
     s->batch = batch_samples;
     s->gain_db = gain_db;
-    s->hist = fm_history_samples(ST_R);
+    s->R = R;
+    s->hist = fm_history_samples(R);
     s->row_bytes = 2 * ((int64_t) s->hist + batch_samples);
     s->d_rows = nullptr;
     s->d_db = nullptr;
@@ -135,10 +146,10 @@ b200_stream* b200_stream_create(int n_streams, int64_t batch_samples, int gain_d
     const size_t ns = (size_t) n_streams;
     bool ok = cudaMalloc(&s->d_rows, ns * (size_t) s->row_bytes) == cudaSuccess;
     ok = ok && cudaMalloc(&s->d_db, sizeof(float) * ns * (size_t) batch_samples) == cudaSuccess;
-    ok = ok && cudaMalloc(&s->d_audio, sizeof(float) * ns * (size_t) (batch_samples / 40)) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_audio, sizeof(float) * ns * (size_t) (batch_samples / (4 * R))) == cudaSuccess;
     ok = ok && cudaHostAlloc(&s->h_in, ns * ST_SLOTS * 2 * (size_t) batch_samples, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&s->h_db, sizeof(float) * ns * ST_SLOTS * (size_t) batch_samples, cudaHostAllocDefault) == cudaSuccess;
-    ok = ok && cudaHostAlloc(&s->h_audio, sizeof(float) * ns * ST_SLOTS * (size_t) (batch_samples / 40), cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&s->h_audio, sizeof(float) * ns * ST_SLOTS * (size_t) (batch_samples / (4 * R)), cudaHostAllocDefault) == cudaSuccess;
     for (int i = 0; ok && i < ST_LANES; ++i) ok = cudaStreamCreateWithFlags(&s->lanes[i], cudaStreamNonBlocking) == cudaSuccess;
     s->st.resize(ns);
     for (size_t i = 0; i < ns; ++i) {
@@ -153,7 +164,7 @@ b200_stream* b200_stream_create(int n_streams, int64_t batch_samples, int gain_d
         }
     }
     if (ok)
-        ok = launch_fm_history_reset(s->d_rows + 2 * (size_t) s->hist, s->row_bytes, n_streams, ST_R, s->lanes[0]) == B200_OK &&
+        ok = launch_fm_history_reset(s->d_rows + 2 * (size_t) s->hist, s->row_bytes, n_streams, R, s->lanes[0]) == B200_OK &&
              cudaStreamSynchronize(s->lanes[0]) == cudaSuccess;
     if (!ok) {
         set_error("stream: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -153,6 +153,56 @@ def test_session_host_buffers(pkg, cuda, po, synth):
     sess.close()
 
 
+@pytest.mark.parametrize("R", [12, 5, 16])
+def test_session_and_stream_other_down_factors(pkg, cuda, po, synth, R):
+    """The reference re-derives R = fs / 192000 when the client sends `bw` (main.c:152-155): the fast-path
+    entry points take it too.  Two batches through a session and chunked pushes through a stream."""
+    torch = cuda
+    tile = int(pkg.lib().b200_chain_tile_samples(R))
+    assert tile % 1024 == 0 and tile % (4 * R) == 0
+    n_streams, n = 3, tile * 4
+    iq = np.stack([synth.s3_fm(2 * n, seed=120 + s) for s in range(n_streams)])
+    want_audio = []
+    for s in range(n_streams):
+        _, dec, _ = po.cic_decimate(R, iq[s])
+        _, _, a, _ = po.fm_demodulate(dec)
+        want_audio.append(a)
+    sess = pkg.Session(n_streams, n, R=R)
+    h_db = np.empty((n_streams, n // 1024, 1024), np.float32)
+    h_audio = np.empty((n_streams, n // (4 * R)), np.float32)
+    parts = []
+    for b in range(2):
+        sess.chain(np.ascontiguousarray(iq[:, b * n:(b + 1) * n]), n, h_db, h_audio)
+        parts.append(h_audio.copy())
+        for s in range(n_streams):
+            rows = po.Spectrum(1024).rows(iq[s, b * n:(b + 1) * n])
+            ok = rows > 1e-6 * rows.mean(axis=1, keepdims=True)
+            assert np.abs(h_db[s][ok] - 10 * np.log10(rows[ok])).max() <= 0.01
+    got = np.concatenate(parts, axis=1)
+    for s in range(n_streams):
+        assert np.abs(got[s] - want_audio[s]).max() <= 1e-4
+    with pytest.raises(pkg.B200Error):
+        sess.chain(np.ascontiguousarray(iq[:, :tile + 8]), tile + 8, h_db, h_audio)
+    sess.close()
+    ps = pkg.PushStream(n_streams, tile * 2, R=R)
+    pos = [0] * n_streams
+    rng = np.random.default_rng(R)
+    while any(p < 2 * n for p in pos):
+        s = int(rng.integers(n_streams))
+        k = min(int(rng.integers(1, 40000)), 2 * n - pos[s])
+        ps.push(s, iq[s, pos[s]:pos[s] + k])
+        pos[s] += k
+    ps.flush()
+    for s in range(n_streams):
+        a = np.concatenate([x for _, x in sorted(ps.audio[s], key=lambda t: t[0])])
+        assert a.shape == want_audio[s].shape and np.abs(a - want_audio[s]).max() <= 1e-4
+        f = np.concatenate([x for _, x in sorted(ps.spectra[s], key=lambda t: t[0])])
+        assert f.shape == (2 * n // 1024, 1024)
+    ps.close()
+    with pytest.raises(pkg.B200Error):
+        pkg.Session(1, 5120, R=300)
+
+
 def test_push_stream_like_a_signal_source_callback(pkg, cuda, po, synth):
     """Three dongles pushing 131072-sample source buffers (signal_source.c:31) in round robin;
     batches of one reference block (204800 samples); sinks receive everything in order."""
