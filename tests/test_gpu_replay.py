@@ -3,7 +3,9 @@ buffers exactly as the reference's signal source hands them to its callbacks; th
 b200_stream_push.  Results against the CPU oracle, for several dongles at once and through the reference's
 unmodified signal_source.c."""
 import ctypes as C
+import json
 import os
+import subprocess
 import threading
 import time
 
@@ -87,3 +89,25 @@ def test_reference_signal_source_drives_the_gpu_path(pkg, cuda, po, synth):
     check_stream(po, iq, frames, audio)
     d.close()
     ps.close()
+
+
+def test_c_host_example_virtual_dongles(pkg, cuda, tmp_path):
+    """examples/virtual_dongles.c: a plain-C host (reader threads as in signal_source.c, rtl_read_async callbacks
+    pushing into b200_stream, sinks cutting wire messages) compiled against the two libraries and run."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "rtl-ws_b200")
+    exe = str(tmp_path / "virtual_dongles")
+    subprocess.run(["gcc", "-O2", "-pthread", "-o", exe, os.path.join(root, "examples", "virtual_dongles.c"),
+                    "-I" + os.path.join(root, "include"), "-L" + lib_dir, "-lb200sdr", "-lb200replay",
+                    "-Wl,-rpath," + lib_dir, "-lm"], check=True)
+    n_dongles, seconds = 5, 1.0
+    out = subprocess.run([exe, str(n_dongles), str(seconds)], check=True, capture_output=True, text=True, timeout=120)
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    n_buffers = int(seconds * 2048000 * 2 / 262144)
+    batches = n_buffers * 131072 // 204800
+    assert r["dongles"] == n_dongles and r["iq_samples"] == n_dongles * n_buffers * 131072
+    assert r["audio_samples"] == n_dongles * batches * 5120
+    assert r["spectrum_messages"] == n_dongles * batches and r["spectrum_bytes"] == r["spectrum_messages"] * (31 + 1024)
+    assert r["audio_messages"] == n_dongles * (batches * 5120 // 4096) and r["audio_bytes"] == r["audio_messages"] * 16392
+    assert 0.1 < r["audio_rms"] < 1.0                      # a 25 kHz-deviation FM signal through the +-1 limiter
+    assert r["kernel_launches"] >= 2 * n_dongles * batches
