@@ -195,6 +195,126 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MULTI ? 2 : 3) spectrum102
     }
 }
 
+// ---- contiguous frames, K = 1 (BASELINE config 2: per-frame spectra of a long capture) ------------------
+// When the frames of a stream follow each other without gap or overlap (hop = row_hop = N, K = 1) the
+// kernel above pays per frame for things that can be paid per six frames: one 2 KB TMA copy, one
+// mbarrier round trip and a lane-0 cursor update per frame and warp.  This variant has the structure
+// of chain_fused.cu without its FM branch: groups of six warps share a four-deep ring of 10 KB tiles
+// (five consecutive frames, ONE bulk copy), full / empty mbarriers; per tile five warps transform a frame
+// each and the sixth (rotating) only re-arms the ring; nobody meets at a block barrier, and one CTA per SM
+// holds two such groups so that the twelve warps spread 3-3-3-3 over the schedulers.  Measured on the same
+// data (256 streams x 8.192 M samples): 744 -> 787 Gsamples/s rectangular, 677 -> 738 Hann; with six frames
+// per tile and all six warps transforming it is 785 / 721.
+constexpr int T6_WARPS = 6;
+constexpr int T6_GROUPS = 2;
+constexpr int T6_THREADS = T6_GROUPS * T6_WARPS * 32;
+constexpr int T6_STAGES = 4;
+constexpr int T6_FRAMES = 5;                       // frames per tile: the sixth warp of the rotation only re-arms the ring
+constexpr int T6_STAGE_BYTES = T6_FRAMES * FRAME_BYTES;
+constexpr int T6_GROUP_SMEM = (T6_STAGES * T6_STAGE_BYTES + T6_WARPS * XCH_BYTES + 64 + 127) / 128 * 128;     // ring, tiles, 8 mbarriers (+pad)
+static_assert(T6_GROUP_SMEM % 128 == 0, "group shared memory must keep the TMA destinations aligned");
+constexpr int T6_SMEM = T6_GROUPS * T6_GROUP_SMEM + N1024 * 4;                        // + window copy
+
+template <bool WINDOW>
+__global__ void __launch_bounds__(T6_THREADS, 1) spectrum1024_tiled_kernel(const SpecParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem_all[];
+    const int lane = threadIdx.x & 31;
+    const int group = (threadIdx.x >> 5) / T6_WARPS;
+    const int warp = (threadIdx.x >> 5) % T6_WARPS;
+    uint8_t* smem = smem_all + group * T6_GROUP_SMEM;
+    uint8_t* ring = smem;
+    float2* xch = reinterpret_cast<float2*>(smem + T6_STAGES * T6_STAGE_BYTES + warp * XCH_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + T6_STAGES * T6_STAGE_BYTES + T6_WARPS * XCH_BYTES);
+    uint64_t* empty = full + T6_STAGES;
+    float* win = reinterpret_cast<float*>(smem_all + T6_GROUPS * T6_GROUP_SMEM);
+
+    const uint32_t n_rows = (uint32_t) p.n_rows;
+    const uint32_t tps = (n_rows + T6_FRAMES - 1) / T6_FRAMES;             // tiles per stream
+    const uint32_t total_tiles = (uint32_t) p.n_streams * tps;
+    const uint32_t first = blockIdx.x * T6_GROUPS + group;
+    const uint32_t stride = gridDim.x * T6_GROUPS;
+    const uint32_t n_mine = first < total_tiles ? (total_tiles - first + stride - 1) / stride : 0;
+
+    auto issue = [&](uint32_t it) {
+        const uint32_t tile = first + it * stride;
+        const uint32_t s = tile / tps;
+        const uint32_t t = tile - s * tps;
+        const uint32_t frames = n_rows - t * T6_FRAMES < (uint32_t) T6_FRAMES ? n_rows - t * T6_FRAMES : (uint32_t) T6_FRAMES;
+        const int st = it % T6_STAGES;
+        const uint8_t* src = p.iq + (int64_t) s * p.stream_stride_bytes + (int64_t) t * T6_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[st], frames * FRAME_BYTES);
+        tma_load_1d(ring + st * T6_STAGE_BYTES, src, frames * FRAME_BYTES, &full[st]);
+    };
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < T6_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], T6_WARPS);
+        }
+        fence_mbar_init();
+        for (uint32_t it = 0; it < T6_STAGES - 1 && it < n_mine; ++it) issue(it);
+    }
+    if (WINDOW) {
+        for (int i = threadIdx.x; i < N1024; i += blockDim.x) win[i] = p.window[i];
+    }
+    __syncthreads();
+
+    float2 tw[32];
+    fft1024_load_twiddles(p.twiddle, lane, tw);
+    const float dboff = p.db_offset - 16.0f * DB_PER_LOG2;
+
+    int service = 0;                      // which warp re-arms the ring for this tile: it mod 6
+    for (uint32_t it = 0; it < n_mine; ++it) {
+        const int st = it % T6_STAGES;
+        const uint32_t tile = first + it * stride;
+        const uint32_t s = tile / tps;
+        const uint32_t t = tile - s * tps;
+        int slot = warp - service - (T6_FRAMES < T6_WARPS ? 1 : 0);       // frames go to the other warps in rotation order
+        if (slot < 0) slot += T6_WARPS;
+        const uint32_t row = t * T6_FRAMES + slot;
+        const bool serving_only = T6_FRAMES < T6_WARPS && warp == service;
+        const bool have = row < n_rows && !serving_only;      // a short last tile leaves some warps without a frame
+
+        mbar_wait(&full[st], (it / T6_STAGES) & 1);
+        if (!serving_only) {
+            c64 a[32];
+            // (a warp without a frame transforms whatever its slot of the stage holds and stores nothing)
+            fft1024_load<WINDOW>(reinterpret_cast<const uint16_t*>(ring + st * T6_STAGE_BYTES + FRAME_BYTES * slot), win, lane, a);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty[st]);
+                if (T6_FRAMES == T6_WARPS && warp == service && it + T6_STAGES - 1 < n_mine) {
+                    if (it > 0) mbar_wait(&empty[(it - 1) % T6_STAGES], ((it - 1) / T6_STAGES) & 1);
+                    fence_proxy_async_smem();
+                    issue(it + T6_STAGES - 1);
+                }
+            }
+            float pw[32];
+            fft1024_core<!WINDOW>(a, tw, xch, lane, pw);
+            // DC-position patch (spectrum.c:30-33): display index 512 takes display index 511's value
+            const float left = __shfl_sync(0xffffffffu, pw[31], 31);
+            if (lane == 0) pw[0] = left;
+            if (have) {
+                float* out = p.db + ((size_t) s * n_rows + row) * N1024 + lane;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) __stcs(out + fft1024_col(q), fmaf(DB_PER_LOG2, lg2_ftz(pw[q]), dboff));
+            }
+        } else {
+            if (lane == 0) {
+                mbar_arrive(&empty[st]);
+                // keep the ring full: tile it + STAGES - 1 goes into the stage tile it - 1 used
+                if (it + T6_STAGES - 1 < n_mine) {
+                    if (it > 0) mbar_wait(&empty[(it - 1) % T6_STAGES], ((it - 1) / T6_STAGES) & 1);
+                    issue(it + T6_STAGES - 1);
+                }
+            }
+            __syncwarp();
+        }
+        service = (service + 1 == T6_WARPS) ? 0 : service + 1;
+    }
+}
+
 }  // namespace
 
 int launch_spectrum1024(const SpecParams& p, cudaStream_t stream)
@@ -207,6 +327,19 @@ int launch_spectrum1024(const SpecParams& p, cudaStream_t stream)
     }
     const bool multi = p.K > 1;
     const bool window = p.window != nullptr;
+    if (!multi && p.hop == N1024 && p.row_hop == N1024 && p.n_rows >= 2 * T6_WARPS && p.db != nullptr && p.power == nullptr &&
+        p.db_u8 == nullptr) {
+        // contiguous frames, dB rows only: six frames per TMA copy (tiles never span streams)
+        auto tkern = window ? spectrum1024_tiled_kernel<true> : spectrum1024_tiled_kernel<false>;
+        if (int rc = ensure_dynamic_smem((const void*) tkern, T6_SMEM)) return rc;
+        const uint64_t tiles = (uint64_t) p.n_streams * (((uint64_t) p.n_rows + T6_FRAMES - 1) / T6_FRAMES);
+        uint64_t tgrid = (uint64_t) sm_count();
+        const uint64_t tneeded = (tiles + T6_GROUPS - 1) / T6_GROUPS;
+        if (tgrid > tneeded) tgrid = tneeded;
+        tkern<<<(unsigned) tgrid, T6_THREADS, T6_SMEM, stream>>>(p);
+        B200_LAUNCH_CHECK();
+        return B200_OK;
+    }
     auto kern = multi ? (window ? spectrum1024_kernel<true, true> : spectrum1024_kernel<true, false>)
                       : (window ? spectrum1024_kernel<false, true> : spectrum1024_kernel<false, false>);
     if (int rc = ensure_dynamic_smem((const void*) kern, CTA_SMEM)) return rc;
