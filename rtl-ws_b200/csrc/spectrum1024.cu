@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MULTI ? 2 : 3) spectrum102
 }
 
 // ---- contiguous frames, K = 1 (BASELINE config 2: per-frame spectra of a long capture) ------------------
-// When the frames of a stream follow each other without gap or overlap (hop = row_hop = N, K = 1) the
+// When the frames of a stream follow each other without gap (hop = row_hop <= N, K = 1: contiguous or overlapping) the
 // kernel above pays per frame for things that can be paid per six frames: one 2 KB TMA copy, one
 // mbarrier round trip and a lane-0 cursor update per frame and warp.  This variant has the structure
 // of chain_fused.cu without its FM branch: groups of six warps share a four-deep ring of 10 KB tiles
@@ -242,9 +242,11 @@ __global__ void __launch_bounds__(T6_THREADS, 1) spectrum1024_tiled_kernel(const
         const uint32_t t = tile - s * tps;
         const uint32_t frames = n_rows - t * T6_FRAMES < (uint32_t) T6_FRAMES ? n_rows - t * T6_FRAMES : (uint32_t) T6_FRAMES;
         const int st = it % T6_STAGES;
-        const uint8_t* src = p.iq + (int64_t) s * p.stream_stride_bytes + (int64_t) t * T6_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[st], frames * FRAME_BYTES);
-        tma_load_1d(ring + st * T6_STAGE_BYTES, src, frames * FRAME_BYTES, &full[st]);
+        // frames of a tile start `hop` samples apart (hop <= N: they may overlap) and arrive as one span
+        const uint32_t bytes = 2u * ((frames - 1) * (uint32_t) p.hop + N1024);
+        const uint8_t* src = p.iq + (int64_t) s * p.stream_stride_bytes + 2 * (int64_t) t * T6_FRAMES * p.hop;
+        mbar_arrive_expect_tx(&full[st], bytes);
+        tma_load_1d(ring + st * T6_STAGE_BYTES, src, bytes, &full[st]);
     };
 
     if (warp == 0 && lane == 0) {
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(T6_THREADS, 1) spectrum1024_tiled_kernel(const
         if (!serving_only) {
             c64 a[32];
             // (a warp without a frame transforms whatever its slot of the stage holds and stores nothing)
-            fft1024_load<WINDOW>(reinterpret_cast<const uint16_t*>(ring + st * T6_STAGE_BYTES + FRAME_BYTES * slot), win, lane, a);
+            fft1024_load<WINDOW>(reinterpret_cast<const uint16_t*>(ring + st * T6_STAGE_BYTES + 2 * p.hop * slot), win, lane, a);
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&empty[st]);
@@ -327,9 +329,9 @@ int launch_spectrum1024(const SpecParams& p, cudaStream_t stream)
     }
     const bool multi = p.K > 1;
     const bool window = p.window != nullptr;
-    if (!multi && p.hop == N1024 && p.row_hop == N1024 && p.n_rows >= 2 * T6_WARPS && p.db != nullptr && p.power == nullptr &&
+    if (!multi && p.hop <= N1024 && p.row_hop == p.hop && p.n_rows >= 2 * T6_WARPS && p.db != nullptr && p.power == nullptr &&
         p.db_u8 == nullptr) {
-        // contiguous frames, dB rows only: six frames per TMA copy (tiles never span streams)
+        // frames hop <= N apart (contiguous or overlapping), dB rows only: five frames per TMA copy (tiles never span streams)
         auto tkern = window ? spectrum1024_tiled_kernel<true> : spectrum1024_tiled_kernel<false>;
         if (int rc = ensure_dynamic_smem((const void*) tkern, T6_SMEM)) return rc;
         const uint64_t tiles = (uint64_t) p.n_streams * (((uint64_t) p.n_rows + T6_FRAMES - 1) / T6_FRAMES);

@@ -273,6 +273,25 @@ def test_full_size_parseval_checksum(pkg, cuda, N):
     assert abs(got.sum().item() / want.sum().item() - 1) < (1e-7 if N == 1024 else 2e-7)
 
 
+@pytest.mark.parametrize("hop,window", [(1024, 0), (512, 1), (256, 1), (1016, 0)])
+def test_n1024_db_only_tiled_path(pkg, cuda, po, synth, hop, window):
+    """dB rows only, K = 1, frames hop <= N apart: the tiled kernel (five frames per TMA copy).  Row counts
+    that are not a multiple of five, several streams, overlap with and without the Hann window."""
+    torch = cuda
+    n_streams, n_rows = 3, 53
+    n = hop * (n_rows - 1) + 1024
+    iqs = np.stack([synth.s2_tones(n, seed=400 + s) for s in range(n_streams)])
+    d = torch.as_tensor(iqs).cuda()
+    plan = pkg.SpectrumPlan(1024, hop=hop, window=window)
+    db = plan.exec(d, db=True)["db"]
+    torch.cuda.synchronize()
+    assert db.shape == (n_streams, n_rows, 1024)
+    db = db.cpu().numpy()
+    for s in range(n_streams):
+        want = po.Spectrum(1024, window=synth.hann(1024) if window else None).rows(iqs[s], hop=hop)
+        check_db(db[s], want)
+
+
 def test_db_only_matches_all_outputs(pkg, cuda, po, synth):
     """Requesting only the dB output must give the same bits as requesting everything, for odd
     row counts and several streams (the outputs are written by separate store loops)."""
