@@ -5,9 +5,9 @@
  *     -> one reader thread each, exactly like signal_source.c's worker (signal_source.c:37-55):
  *        rtl_read_async(dev, callback, ctx), 262144-byte buffers
  *     -> the callback body is b200_stream_push (libb200sdr.so): H2D, fused chain kernel, D2H, asynchronously
- *     -> sinks on the reader thread: per-frame dB spectra are averaged over the reference's 6 frames and cut
- *        to the payload bytes of cbb_main.c:121-130, audio is packed into the websocket messages of
- *        main.c:86-110 (b200_wire_*), and both are counted / checksummed instead of being sent.
+ *     -> sinks on the reader thread: the 6-frame averaged payload bytes of cbb_main.c:121-130 (computed on the
+ *        GPU) become spectrum messages, audio is packed into the websocket messages of main.c:86-110
+ *        (b200_wire_*), and both are counted / checksummed instead of being sent.
  *
  * Each dongle gets its own b200_stream (the push API is single-producer, as the reference's source is).
  *
@@ -64,20 +64,13 @@ static void synth_fm(uint8_t* iq, int64_t n, unsigned seed)
     }
 }
 
-/* spectrum sink: the first 6 frames of a batch -> averaged u8 payload (cbb_main.c:48-59,121-130) -> message */
-static void on_spectra(void* user, int stream, int64_t first_frame, int n_frames, const float* db)
+/* payload sink: the 6-frame average of cbb_main.c:48-59,121-130, computed on the GPU -> one websocket message */
+static void on_payload(void* user, int stream, int64_t first_frame, int k, const uint8_t* payload)
 {
     struct dongle* d = (struct dongle*) user;
-    uint8_t payload[1024];
     (void) stream;
     (void) first_frame;
-    if (n_frames < 6) return;
-    for (int i = 0; i < 1024; ++i) {
-        double p = 0.0;
-        for (int k = 0; k < 6; ++k) p += pow(10.0, db[k * 1024 + i] / 10.0);
-        int m = (int) (10.0 * log10(p / 6.0));
-        payload[i] = (uint8_t) (m < 0 ? 0 : (m > 255 ? 255 : m));
-    }
+    (void) k;
     const int n = b200_wire_spectrum_message(d->message, (int) sizeof(d->message), rtl_freq(d->dev), rtl_sample_rate(d->dev), 0,
                                              payload, 1024);
     if (n > 0) {
@@ -150,7 +143,8 @@ int main(int argc, char** argv)
             fprintf(stderr, "b200_stream_create: %s\n", b200_last_error());
             return 1;
         }
-        b200_stream_set_sinks(d->gpu, on_spectra, on_audio, d);
+        b200_stream_set_sinks(d->gpu, NULL, on_audio, d);              /* no per-frame rows: they stay on the device */
+        b200_stream_set_payload_sink(d->gpu, 6, on_payload);          /* FFT_AVERAGE, cbb_main.c:18 */
     }
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);

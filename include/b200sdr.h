@@ -181,6 +181,12 @@ b200_stream* b200_stream_create(int n_streams, int64_t batch_samples, int gain_d
 b200_stream* b200_stream_create_r(int n_streams, int64_t batch_samples, int gain_db, int R);
 void b200_stream_destroy(b200_stream* s);
 void b200_stream_set_sinks(b200_stream* s, b200_spectrum_sink spectrum_sink, b200_audio_sink audio_sink, void* user);
+/* What the reference actually sends its client: the K-frame average at the start of every batch as the 1024 payload
+ * bytes of cbb_main.c:121-130 (zero a row, add K frames, 10*log10(|g * P / K|), truncate, clamp), computed on the
+ * device (1 KB per batch over PCIe).  With a payload sink and a NULL spectrum sink the per-frame dB rows (4 bytes
+ * per sample) stay on the device.  K = 6 is the reference's FFT_AVERAGE (cbb_main.c:18).  Call before the first push. */
+typedef void (*b200_payload_sink)(void* user, int stream, int64_t first_frame, int n_frames_averaged, const uint8_t* payload);
+int b200_stream_set_payload_sink(b200_stream* s, int K, b200_payload_sink sink);
 /* samples: len interleaved (re, im) byte pairs, i.e. a `const cmplx_u8*` */
 int b200_stream_push(b200_stream* s, int stream, const uint8_t* samples, int len);
 int b200_stream_poll(b200_stream* s);           /* deliver whatever has finished, never blocks */

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "b200_fm_history_samples", "b200_fm_history_reset", "b200_fm_history_carry", "b200_fm_exec",
     "b200_chain_exec", "b200_chain_exec_r", "b200_chain_tile_samples",
     "b200_session_create", "b200_session_create_r", "b200_session_destroy", "b200_session_reset", "b200_session_chain",
-    "b200_stream_create", "b200_stream_create_r", "b200_stream_destroy", "b200_stream_set_sinks", "b200_stream_push", "b200_stream_poll",
+    "b200_stream_create", "b200_stream_create_r", "b200_stream_destroy", "b200_stream_set_sinks", "b200_stream_set_payload_sink", "b200_stream_push", "b200_stream_poll",
     "b200_stream_flush", "b200_stream_pending_samples",
     "b200_wire_spectrum_header", "b200_wire_spectrum_message", "b200_wire_spectrum_messages",
     "b200_wire_audio_messages", "b200_wire_audio_fragment", "b200_wire_reference_drain_index",
@@ -56,6 +56,7 @@ class CicDelayLine(C.Structure):
 RF_CALLBACK = C.CFUNCTYPE(None, C.POINTER(CmplxS32), C.c_int)
 SPECTRUM_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_float))
 AUDIO_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_float))
+PAYLOAD_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_ubyte))
 
 _lib = None
 
@@ -103,6 +104,7 @@ def lib() -> C.CDLL:
     L.b200_stream_destroy.argtypes = [vp]
     L.b200_stream_set_sinks.restype = None
     L.b200_stream_set_sinks.argtypes = [vp, SPECTRUM_SINK, AUDIO_SINK, vp]
+    L.b200_stream_set_payload_sink.argtypes = [vp, i32, PAYLOAD_SINK]
     L.b200_stream_push.argtypes = [vp, i32, vp, i32]
     L.b200_stream_poll.argtypes = [vp]
     L.b200_stream_flush.argtypes = [vp]
@@ -351,12 +353,18 @@ class Session:
 class PushStream:
     """b200_stream_*: signal_source-style pushes in, spectra and audio out through sinks."""
 
-    def __init__(self, n_streams: int, batch_samples: int, gain_db: int = 0, R: int = 10):
+    def __init__(self, n_streams: int, batch_samples: int, gain_db: int = 0, R: int = 10, payload_K: int = 0,
+                 frames: bool = True):
+        """payload_K > 0: also collect the K-frame averaged u8 payload of every batch (self.payloads);
+        frames=False: no per-frame dB sink (the rows stay on the device)."""
         _torch()
         self.n_streams, self.batch, self.R = n_streams, batch_samples, R
         self.h = lib().b200_stream_create_r(n_streams, batch_samples, gain_db, R)
         if not self.h:
             raise B200Error(f"b200_stream_create_r: {last_error()}")
+        self.payloads = [[] for _ in range(n_streams)]     # (first_frame, K, [1024] u8 copy)
+        self._frames = frames
+        self._payload_K = payload_K
         self.spectra = [[] for _ in range(n_streams)]      # (first_frame, [n_frames, 1024] copy)
         self.audio = [[] for _ in range(n_streams)]        # (first_sample, [n] copy)
 
@@ -366,8 +374,13 @@ class PushStream:
         def on_audio(user, stream, first, n, ptr):
             self.audio[stream].append((first, np.ctypeslib.as_array(ptr, shape=(n,)).copy()))
 
-        self._cb = (SPECTRUM_SINK(on_spectrum), AUDIO_SINK(on_audio))
+        def on_payload(user, stream, first, k, ptr):
+            self.payloads[stream].append((first, k, np.ctypeslib.as_array(ptr, shape=(1024,)).copy()))
+
+        self._cb = (SPECTRUM_SINK(on_spectrum) if self._frames else SPECTRUM_SINK(), AUDIO_SINK(on_audio), PAYLOAD_SINK(on_payload))
         lib().b200_stream_set_sinks(self.h, self._cb[0], self._cb[1], None)
+        if self._payload_K > 0:
+            _check(lib().b200_stream_set_payload_sink(self.h, self._payload_K, self._cb[2]), "b200_stream_set_payload_sink")
 
     def push(self, stream: int, samples: np.ndarray) -> None:
         samples = np.ascontiguousarray(samples, dtype=np.uint8)

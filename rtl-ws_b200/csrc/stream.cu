@@ -44,6 +44,10 @@ struct b200_stream {
     uint8_t* h_in;                 // pinned [n_streams][ST_SLOTS][2 * batch]
     float* h_db;                   // pinned [n_streams][ST_SLOTS][batch]
     float* h_audio;                // pinned [n_streams][ST_SLOTS][batch / (4R)]
+    uint8_t* d_payload;            // [n_streams][1024]: K-frame averaged payload bytes of the batch start
+    uint8_t* h_payload;            // pinned [n_streams][ST_SLOTS][1024]
+    int payload_K;                 // 0 = no payload sink
+    b200_payload_sink payload_sink;
     cudaStream_t lanes[ST_LANES];
     struct PerStream {
         int64_t fill;              // samples in the current slot
@@ -72,6 +76,8 @@ static void stream_deliver(b200_stream* s, int i, bool block)
         }
         const int64_t b = p.batches_delivered;
         const size_t off = ((size_t) i * ST_SLOTS + slot);
+        if (s->payload_sink && s->payload_K > 0)
+            s->payload_sink(s->user, i, b * (s->batch / 1024), s->payload_K, s->h_payload + off * 1024);
         if (s->spectrum_sink)
             s->spectrum_sink(s->user, i, b * (s->batch / 1024), (int) (s->batch / 1024), s->h_db + off * (size_t) s->batch);
         if (s->audio_sink)
@@ -92,12 +98,20 @@ static int stream_submit(b200_stream* s, int i)
     float* d_audio = s->d_audio + (size_t) i * (size_t) (s->batch / (4 * s->R));
     B200_CUDA_TRY(cudaMemcpyAsync(d_batch, s->h_in + off * 2 * (size_t) s->batch, 2 * (size_t) s->batch,
                                   cudaMemcpyHostToDevice, lane));
-    int rc = b200_chain_exec_r(d_batch, s->row_bytes, 1, s->batch, s->R, s->gain_db, d_db, d_audio, s->batch / (4 * s->R), nullptr, 0, lane);
+    const bool want_payload = s->payload_sink != nullptr && s->payload_K > 0;
+    uint8_t* d_pay = s->d_payload + (size_t) i * 1024;
+    // without a per-frame sink the dB rows are not computed at all: the FM kernel and the K-frame average only
+    int rc = b200_chain_exec_r(d_batch, s->row_bytes, 1, s->batch, s->R, s->gain_db, s->spectrum_sink ? d_db : nullptr, d_audio,
+                               s->batch / (4 * s->R), want_payload ? d_pay : nullptr, want_payload ? s->payload_K : 0, lane);
     if (rc) return rc;
     rc = launch_fm_history_carry(d_batch, s->row_bytes, 1, s->batch, s->R, lane);
     if (rc) return rc;
-    B200_CUDA_TRY(cudaMemcpyAsync(s->h_db + off * (size_t) s->batch, d_db, sizeof(float) * (size_t) s->batch,
-                                  cudaMemcpyDeviceToHost, lane));
+    // the per-frame dB rows cross PCIe only if somebody listens (4 bytes per sample; the payload is 1 KB per batch)
+    if (s->spectrum_sink)
+        B200_CUDA_TRY(cudaMemcpyAsync(s->h_db + off * (size_t) s->batch, d_db, sizeof(float) * (size_t) s->batch,
+                                      cudaMemcpyDeviceToHost, lane));
+    if (want_payload)
+        B200_CUDA_TRY(cudaMemcpyAsync(s->h_payload + off * 1024, d_pay, 1024, cudaMemcpyDeviceToHost, lane));
     B200_CUDA_TRY(cudaMemcpyAsync(s->h_audio + off * (size_t) (s->batch / (4 * s->R)), d_audio,
                                   sizeof(float) * (size_t) (s->batch / (4 * s->R)), cudaMemcpyDeviceToHost, lane));
     B200_CUDA_TRY(cudaEventRecord(p.done[slot], lane));
@@ -139,6 +153,10 @@ b200_stream* b200_stream_create_r(int n_streams, int64_t batch_samples, int gain
     s->h_in = nullptr;
     s->h_db = nullptr;
     s->h_audio = nullptr;
+    s->d_payload = nullptr;
+    s->h_payload = nullptr;
+    s->payload_K = 0;
+    s->payload_sink = nullptr;
     s->spectrum_sink = nullptr;
     s->audio_sink = nullptr;
     s->user = nullptr;
@@ -150,6 +168,8 @@ b200_stream* b200_stream_create_r(int n_streams, int64_t batch_samples, int gain
     ok = ok && cudaHostAlloc(&s->h_in, ns * ST_SLOTS * 2 * (size_t) batch_samples, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&s->h_db, sizeof(float) * ns * ST_SLOTS * (size_t) batch_samples, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&s->h_audio, sizeof(float) * ns * ST_SLOTS * (size_t) (batch_samples / (4 * R)), cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_payload, ns * 1024) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&s->h_payload, ns * ST_SLOTS * 1024, cudaHostAllocDefault) == cudaSuccess;
     for (int i = 0; ok && i < ST_LANES; ++i) ok = cudaStreamCreateWithFlags(&s->lanes[i], cudaStreamNonBlocking) == cudaSuccess;
     s->st.resize(ns);
     for (size_t i = 0; i < ns; ++i) {
@@ -191,6 +211,8 @@ void b200_stream_destroy(b200_stream* s)
     if (s->h_in) cudaFreeHost(s->h_in);
     if (s->h_db) cudaFreeHost(s->h_db);
     if (s->h_audio) cudaFreeHost(s->h_audio);
+    if (s->d_payload) cudaFree(s->d_payload);
+    if (s->h_payload) cudaFreeHost(s->h_payload);
     delete s;
 }
 
@@ -199,6 +221,17 @@ void b200_stream_set_sinks(b200_stream* s, b200_spectrum_sink spectrum_sink, b20
     s->spectrum_sink = spectrum_sink;
     s->audio_sink = audio_sink;
     s->user = user;
+}
+
+int b200_stream_set_payload_sink(b200_stream* s, int K, b200_payload_sink sink)
+{
+    if (s == nullptr || K < 0 || (int64_t) K * 1024 > s->batch) {
+        set_error("stream payload sink: K = %d frames do not fit a batch", K);
+        return B200_ERR_ARG;
+    }
+    s->payload_K = sink ? K : 0;
+    s->payload_sink = sink;
+    return B200_OK;
 }
 
 int b200_stream_push(b200_stream* s, int stream, const uint8_t* samples, int len)

@@ -203,6 +203,31 @@ def test_session_and_stream_other_down_factors(pkg, cuda, po, synth, R):
         pkg.Session(1, 5120, R=300)
 
 
+def test_push_stream_payload_sink(pkg, cuda, po, synth):
+    """What the reference sends its client: the 6-frame average at the start of every batch as payload bytes
+    (cbb_main.c:48-59,121-130), computed on the device; the per-frame rows are neither computed nor copied."""
+    n_streams, batch, n_batches, gain = 2, 204800, 3, 17
+    iq = np.stack([synth.s2_tones(batch * n_batches, seed=140 + s) for s in range(n_streams)])
+    ps = pkg.PushStream(n_streams, batch, gain_db=gain, payload_K=6, frames=False)
+    for s in range(n_streams):
+        for pos in range(0, batch * n_batches, 131072):
+            ps.push(s, iq[s, pos:pos + 131072])
+    ps.flush()
+    for s in range(n_streams):
+        assert ps.spectra[s] == [] and len(ps.payloads[s]) == n_batches
+        for b, (first, k, payload) in enumerate(sorted(ps.payloads[s], key=lambda t: t[0])):
+            assert first == b * (batch // 1024) and k == 6
+            rows = po.Spectrum(1024).rows(iq[s, b * batch:b * batch + 6 * 1024], K=6)
+            want, dbf = po.db_payload(rows[0], 6, gain)
+            diff = payload != want
+            assert diff.mean() < 0.01 and (np.abs(dbf[diff] - np.rint(dbf[diff])) <= 0.01).all()
+        _, dec, _ = po.cic_decimate(10, iq[s])
+        _, _, want_audio, _ = po.fm_demodulate(dec)
+        a = np.concatenate([x for _, x in sorted(ps.audio[s], key=lambda t: t[0])])
+        assert np.abs(a - want_audio).max() <= 1e-4
+    ps.close()
+
+
 def test_push_stream_like_a_signal_source_callback(pkg, cuda, po, synth):
     """Three dongles pushing 131072-sample source buffers (signal_source.c:31) in round robin;
     batches of one reference block (204800 samples); sinks receive everything in order."""
