@@ -79,6 +79,7 @@ int cached_occupancy(const void* kernel, int block_threads, int smem_bytes)
 int launch_spectrum1024(const SpecParams& p, cudaStream_t stream);
 int launch_spectrum_generic(const SpecParams& p, int N, int kind, cudaStream_t stream);
 int launch_spectrum4096(const SpecParams& p, cudaStream_t stream);
+int launch_spectrum2048(const SpecParams& p, cudaStream_t stream);
 int launch_spectrum_mx1024(const SpecParams& p, int N, cudaStream_t stream);
 int launch_spectrum64k(const SpecParams& p, const Spec64kExtra& x, cudaStream_t stream);
 int launch_fm_chain(const FmParams& p, cudaStream_t stream);
@@ -102,6 +103,7 @@ struct b200_spectrum_plan {
     float2* d_twiddle1024;         // 1024-point table (N = 2048 / 4096 / 8192 run M branches of 1024)
     float2* d_twiddle_rk;          // [M][1024]: W_N^(r k), the layout spectrum_mx1024.cu reads with immediate offsets
     float2* d_twiddle_4k;          // N = 4096: [64][64] W_4096^(n2 k1), the inter-pass table of spectrum4096.cu
+                                   // N = 2048: [32][64] W_2048^(n2 k1), the inter-pass table of spectrum2048.cu
     float* d_window;
     Spec64kExtra x64;              // N = 65536 only (all null otherwise)
     int device;
@@ -235,11 +237,12 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
             return nullptr;
         }
     }
-    if (N == 4096) {
-        std::vector<float2> t4((size_t) 64 * 64);
-        for (int n2 = 0; n2 < 64; ++n2)
+    if (N == 4096 || N == 2048) {
+        const int rows = N / 64;                                    // n2 = 0..rows-1, k1 = 0..63
+        std::vector<float2> t4((size_t) rows * 64);
+        for (int n2 = 0; n2 < rows; ++n2)
             for (int k1 = 0; k1 < 64; ++k1) {
-                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double) (n2 * k1) / 4096.0L;
+                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double) (n2 * k1) / (long double) N;
                 t4[(size_t) n2 * 64 + k1] = make_float2((float) cosl(a), (float) sinl(a));
             }
         if (cudaMalloc((void**) &pl->d_twiddle_4k, sizeof(float2) * t4.size()) != cudaSuccess ||
@@ -343,6 +346,10 @@ static int spectrum_exec_kind(b200_spectrum_plan* plan, const void* d_in, int64_
         if (plan->N == 4096) {
             p.twiddle_n = plan->d_twiddle_4k;
             return launch_spectrum4096(p, stream);
+        }
+        if (plan->N == 2048) {
+            p.twiddle_n = plan->d_twiddle_4k;
+            return launch_spectrum2048(p, stream);
         }
         return launch_spectrum_mx1024(p, plan->N, stream);
     }

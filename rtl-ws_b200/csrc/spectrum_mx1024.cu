@@ -1,8 +1,9 @@
 // spectrum_mx1024.cu -- batched power spectra for N = M * 1024, M in {2, 4, 8} (sm_100a):
 // the frame lengths between the reference's 1024 and what still fits one CTA's shared memory.
-// The library routes N = 2048 and 8192 here; 4096 (BASELINE config 2's second size) has its own
-// kernel with a single shared-memory round trip, spectrum4096.cu, and M = 4 is kept as the
-// general form (it is what that kernel was measured against: 490 vs 574 Gsamples/s).
+// The library routes N = 8192 here; 2048 and 4096 (BASELINE config 2's second size) have their own
+// kernels with a single shared-memory round trip (spectrum2048.cu, spectrum4096.cu); M = 2 and 4 are
+// kept as the general form (what those kernels were measured against: 517 vs 637 and 490 vs 675
+// Gsamples/s).
 //
 // Decimation in time by M:  X[k + 1024 q] = sum_{r<M} W_M^(r q) * ( W_N^(r k) * F_r[k] ),
 // F_r = the 1024-point transform of the polyphase branch x[M m + r].  A CTA is M warps:

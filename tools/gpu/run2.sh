@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/kbench.py --streams 256 > gpurun_out/r01c_kbench.log 2>&1; cat gpurun_out/r01c_kbench.log
-python tools/kbench.py --streams 256 --samples 8192000 --only spectrum1024_db
-python tools/kbench.py --streams 256 --samples 8192000 --only spectrum4096_db
-python tools/kbench.py --streams 256 --samples 8192000 --only chain_fused
+python -m pytest tests/test_gpu_spectrum.py -x -q 2>&1 | tail -3
+python tools/kbench.py --only spectrum2048_db --streams 256
+python tools/kbench.py --only spectrum2048_db --streams 256 --samples 8192000
