@@ -40,6 +40,8 @@ rows64k = plan64k.rows(L)
 db64k = torch.empty((S, rows64k, 65536), dtype=torch.float32, device="cuda")
 plan1k_h = pkg.SpectrumPlan(1024, window=pkg.WINDOW_HANN)
 plan4k_h = pkg.SpectrumPlan(4096, window=pkg.WINDOW_HANN)
+plan8k = pkg.SpectrumPlan(8192)
+db8k = torch.empty((S, L // 8192, 8192), dtype=torch.float32, device="cuda")
 plan2k = pkg.SpectrumPlan(2048)
 db2k = torch.empty((S, L // 2048, 2048), dtype=torch.float32, device="cuda")
 
@@ -52,6 +54,7 @@ cases = {
     "spectrum1024_hann_db": (lambda: plan1k_h.exec(ring.batch, db=True, out=out), 6.0),
     "spectrum4096_hann_db": (lambda: plan4k_h.exec(ring.batch, db=True, out={"db": db4k}), 6.0),
     "spectrum2048_db": (lambda: plan2k.exec(ring.batch, db=True, out={"db": db2k}), 6.0),
+    "spectrum8192_db": (lambda: plan8k.exec(ring.batch, db=True, out={"db": db8k}), 6.0),
     "spectrum65536_hann_50pct": (lambda: plan64k.exec(ring.batch, db=True, out={"db": db64k}), 10.0),
 }
 for name, (fn, bps) in cases.items():
