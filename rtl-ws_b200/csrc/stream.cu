@@ -7,7 +7,12 @@
 // without blocking: cudaMemcpyAsync to the stream's device row [history | batch], the fused
 // chain kernel for that row, the history carry, and asynchronous copies of the dB rows and
 // the audio back into pinned result buffers -- all on one of a small pool of CUDA streams,
-// so batches of different dongles overlap.  Results are handed to the caller's sinks from
+// so batches of different dongles overlap.  Dongles that run in step (the usual case: same sample rate, same
+// buffer size) fill their batches at the same time, so full slots are submitted in RUNS: when every stream
+// of a group of up to 16 consecutive streams has its batch ready, the group goes out as one 2-D copy, one
+// kernel launch over the group's rows and 2-D copies back -- seven CUDA calls per group instead of per stream.
+// A stream that gets ahead of its group (its second slot fills) is submitted on its own, and poll / flush
+// submit whatever is ready.  Results are handed to the caller's sinks from
 // b200_stream_push / _poll / _flush on the calling thread (no hidden threads), in submission
 // order per stream.  Re-blocking is aligned to stream start like rf_decimator.c:88-115, so
 // results do not depend on how the source chunks the samples.
@@ -29,6 +34,7 @@ namespace {
 constexpr int ST_R = 10;
 constexpr int ST_SLOTS = 2;
 constexpr int ST_LANES = 4;
+constexpr int ST_GROUP = 16;       // streams submitted together when all of them are ready
 }  // namespace
 
 struct b200_stream {
@@ -56,6 +62,7 @@ struct b200_stream {
         int64_t batches_delivered;
         cudaEvent_t done[ST_SLOTS];
         bool in_flight[ST_SLOTS];
+        bool ready[ST_SLOTS];      // full, not yet submitted
     };
     std::vector<PerStream> st;
     b200_spectrum_sink spectrum_sink;
@@ -87,38 +94,85 @@ static void stream_deliver(b200_stream* s, int i, bool block)
     }
 }
 
-static int stream_submit(b200_stream* s, int i)
+// Submit the ready slot `slot` of streams [a, b) as one unit.  All of them run on the lane of their group, so
+// the batches of one stream stay ordered (the history carry of batch n precedes the copy of batch n + 1).
+static int stream_submit_run(b200_stream* s, int a, int b, int slot)
 {
-    b200_stream::PerStream& p = s->st[i];
-    const int slot = p.slot;
-    const size_t off = ((size_t) i * ST_SLOTS + slot);
-    cudaStream_t lane = s->lanes[i % ST_LANES];
-    uint8_t* d_batch = s->d_rows + (size_t) i * (size_t) s->row_bytes + 2 * (size_t) s->hist;
-    float* d_db = s->d_db + (size_t) i * (size_t) s->batch;
-    float* d_audio = s->d_audio + (size_t) i * (size_t) (s->batch / (4 * s->R));
-    B200_CUDA_TRY(cudaMemcpyAsync(d_batch, s->h_in + off * 2 * (size_t) s->batch, 2 * (size_t) s->batch,
-                                  cudaMemcpyHostToDevice, lane));
+    const int n = b - a;
+    const size_t batch = (size_t) s->batch;
+    const size_t n_audio = batch / (size_t) (4 * s->R);
+    cudaStream_t lane = s->lanes[(a / ST_GROUP) % ST_LANES];
+    const size_t off = (size_t) a * ST_SLOTS + (size_t) slot;            // first stream's slot; next stream: + ST_SLOTS
+    uint8_t* d_batch = s->d_rows + (size_t) a * (size_t) s->row_bytes + 2 * (size_t) s->hist;
+    float* d_db = s->d_db + (size_t) a * batch;
+    float* d_audio = s->d_audio + (size_t) a * n_audio;
+    uint8_t* d_pay = s->d_payload + (size_t) a * 1024;
     const bool want_payload = s->payload_sink != nullptr && s->payload_K > 0;
-    uint8_t* d_pay = s->d_payload + (size_t) i * 1024;
+    B200_CUDA_TRY(cudaMemcpy2DAsync(d_batch, (size_t) s->row_bytes, s->h_in + off * 2 * batch, ST_SLOTS * 2 * batch, 2 * batch,
+                                    (size_t) n, cudaMemcpyHostToDevice, lane));
     // without a per-frame sink the dB rows are not computed at all: the FM kernel and the K-frame average only
-    int rc = b200_chain_exec_r(d_batch, s->row_bytes, 1, s->batch, s->R, s->gain_db, s->spectrum_sink ? d_db : nullptr, d_audio,
-                               s->batch / (4 * s->R), want_payload ? d_pay : nullptr, want_payload ? s->payload_K : 0, lane);
+    int rc = b200_chain_exec_r(d_batch, s->row_bytes, n, s->batch, s->R, s->gain_db, s->spectrum_sink ? d_db : nullptr, d_audio,
+                               (int64_t) n_audio, want_payload ? d_pay : nullptr, want_payload ? s->payload_K : 0, lane);
     if (rc) return rc;
-    rc = launch_fm_history_carry(d_batch, s->row_bytes, 1, s->batch, s->R, lane);
+    rc = launch_fm_history_carry(d_batch, s->row_bytes, n, s->batch, s->R, lane);
     if (rc) return rc;
     // the per-frame dB rows cross PCIe only if somebody listens (4 bytes per sample; the payload is 1 KB per batch)
     if (s->spectrum_sink)
-        B200_CUDA_TRY(cudaMemcpyAsync(s->h_db + off * (size_t) s->batch, d_db, sizeof(float) * (size_t) s->batch,
-                                      cudaMemcpyDeviceToHost, lane));
+        B200_CUDA_TRY(cudaMemcpy2DAsync(s->h_db + off * batch, ST_SLOTS * batch * sizeof(float), d_db, batch * sizeof(float),
+                                        batch * sizeof(float), (size_t) n, cudaMemcpyDeviceToHost, lane));
+    B200_CUDA_TRY(cudaMemcpy2DAsync(s->h_audio + off * n_audio, ST_SLOTS * n_audio * sizeof(float), d_audio,
+                                    n_audio * sizeof(float), n_audio * sizeof(float), (size_t) n, cudaMemcpyDeviceToHost, lane));
     if (want_payload)
-        B200_CUDA_TRY(cudaMemcpyAsync(s->h_payload + off * 1024, d_pay, 1024, cudaMemcpyDeviceToHost, lane));
-    B200_CUDA_TRY(cudaMemcpyAsync(s->h_audio + off * (size_t) (s->batch / (4 * s->R)), d_audio,
-                                  sizeof(float) * (size_t) (s->batch / (4 * s->R)), cudaMemcpyDeviceToHost, lane));
-    B200_CUDA_TRY(cudaEventRecord(p.done[slot], lane));
-    p.in_flight[slot] = true;
-    ++p.batches_submitted;
-    p.slot = (slot + 1) % ST_SLOTS;
-    p.fill = 0;
+        B200_CUDA_TRY(cudaMemcpy2DAsync(s->h_payload + off * 1024, ST_SLOTS * 1024, d_pay, 1024, 1024, (size_t) n,
+                                        cudaMemcpyDeviceToHost, lane));
+    for (int i = a; i < b; ++i) {
+        b200_stream::PerStream& p = s->st[i];
+        B200_CUDA_TRY(cudaEventRecord(p.done[slot], lane));
+        p.ready[slot] = false;
+        p.in_flight[slot] = true;
+        ++p.batches_submitted;
+    }
+    return B200_OK;
+}
+
+// the slot stream i would submit next (its oldest full one), or -1
+static int stream_ready_slot(const b200_stream* s, int i)
+{
+    const b200_stream::PerStream& p = s->st[i];
+    const int slot = (int) (p.batches_submitted % ST_SLOTS);
+    return p.ready[slot] ? slot : -1;
+}
+
+// submit the whole group of stream i if every member is ready with the same slot; returns 1 if it went out
+static int stream_try_group(b200_stream* s, int i)
+{
+    const int a = (i / ST_GROUP) * ST_GROUP;
+    const int b = a + ST_GROUP < s->n_streams ? a + ST_GROUP : s->n_streams;
+    const int slot = stream_ready_slot(s, a);
+    if (slot < 0) return 0;
+    for (int k = a + 1; k < b; ++k)
+        if (stream_ready_slot(s, k) != slot) return 0;
+    const int rc = stream_submit_run(s, a, b, slot);
+    return rc ? rc : 1;
+}
+
+// submit everything that is ready, in maximal runs of consecutive streams of one group with the same slot
+static int stream_submit_ready(b200_stream* s)
+{
+    int i = 0;
+    while (i < s->n_streams) {
+        const int slot = stream_ready_slot(s, i);
+        if (slot < 0) {
+            ++i;
+            continue;
+        }
+        const int group_end = (i / ST_GROUP + 1) * ST_GROUP < s->n_streams ? (i / ST_GROUP + 1) * ST_GROUP : s->n_streams;
+        int j = i + 1;
+        while (j < group_end && stream_ready_slot(s, j) == slot) ++j;
+        const int rc = stream_submit_run(s, i, j, slot);
+        if (rc) return rc;
+        // the same stream may hold a second full slot: look at it again
+    }
     return B200_OK;
 }
 
@@ -180,6 +234,7 @@ b200_stream* b200_stream_create_r(int n_streams, int64_t batch_samples, int gain
         for (int k = 0; k < ST_SLOTS; ++k) {
             s->st[i].done[k] = nullptr;
             s->st[i].in_flight[k] = false;
+            s->st[i].ready[k] = false;
             if (ok) ok = cudaEventCreateWithFlags(&s->st[i].done[k], cudaEventDisableTiming) == cudaSuccess;
         }
     }
@@ -244,7 +299,12 @@ int b200_stream_push(b200_stream* s, int stream, const uint8_t* samples, int len
     const uint8_t* src = samples;
     int64_t remaining = len;
     while (remaining > 0) {
-        // the slot about to be written must have been delivered (two batches in flight at most)
+        // the slot about to be written must be free: a batch still waiting for its group goes out on its own,
+        // a batch in flight is waited for and delivered (two batches per stream at most)
+        if (p.fill == 0 && p.ready[p.slot]) {
+            const int rc = stream_submit_run(s, stream, stream + 1, p.slot);
+            if (rc) return rc;
+        }
         if (p.fill == 0 && p.in_flight[p.slot]) stream_deliver(s, stream, true);
         const int64_t room = s->batch - p.fill;
         const int64_t n = remaining < room ? remaining : room;
@@ -254,8 +314,11 @@ int b200_stream_push(b200_stream* s, int stream, const uint8_t* samples, int len
         p.fill += n;
         remaining -= n;
         if (p.fill == s->batch) {
-            const int rc = stream_submit(s, stream);
-            if (rc) return rc;
+            p.ready[p.slot] = true;
+            p.slot = (p.slot + 1) % ST_SLOTS;
+            p.fill = 0;
+            const int rc = stream_try_group(s, stream);
+            if (rc < 0) return rc;
         }
     }
     stream_deliver(s, stream, false);
@@ -265,6 +328,7 @@ int b200_stream_push(b200_stream* s, int stream, const uint8_t* samples, int len
 int b200_stream_poll(b200_stream* s)
 {
     if (s == nullptr) return B200_ERR_ARG;
+    if (int rc = stream_submit_ready(s)) return rc;         // batches waiting for a slower member of their group
     for (int i = 0; i < s->n_streams; ++i) stream_deliver(s, i, false);
     return B200_OK;
 }
@@ -272,6 +336,7 @@ int b200_stream_poll(b200_stream* s)
 int b200_stream_flush(b200_stream* s)
 {
     if (s == nullptr) return B200_ERR_ARG;
+    if (int rc = stream_submit_ready(s)) return rc;
     for (int i = 0; i < s->n_streams; ++i) stream_deliver(s, i, true);
     return B200_OK;
 }

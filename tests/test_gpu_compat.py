@@ -203,6 +203,39 @@ def test_session_and_stream_other_down_factors(pkg, cuda, po, synth, R):
         pkg.Session(1, 5120, R=300)
 
 
+def test_push_stream_groups_and_stragglers(pkg, cuda, po, synth):
+    """Full batches are submitted in runs when a whole group of (up to 16) streams is ready; a stream that runs
+    ahead of its group goes out on its own, and poll() submits what is waiting.  20 streams = two groups; stream 5
+    pushes three batches before anybody else starts, stream 18 never finishes its last batch."""
+    n_streams, batch = 20, 5120 * 4
+    n = batch * 3
+    iq = np.stack([synth.s3_fm(n, seed=160 + s) for s in range(n_streams)])
+    ps = pkg.PushStream(n_streams, batch)
+    before = pkg.launch_count()
+    ps.push(5, iq[5])                                    # three batches: the third forces the first out alone
+    assert ps.pending(5) == 0
+    for b in range(3):
+        for s in range(n_streams):
+            if s == 5:
+                continue
+            hi = (b + 1) * batch if not (s == 18 and b == 2) else (b + 1) * batch - 1000
+            ps.push(s, iq[s, b * batch:hi])
+        ps.poll()
+    ps.flush()
+    launches = pkg.launch_count() - before
+    assert launches < 2 * 3 * n_streams, launches          # far fewer than two launches per stream and batch
+    assert ps.pending(18) == batch - 1000
+    for s in range(n_streams):
+        n_done = 2 * batch if s == 18 else n
+        _, dec, _ = po.cic_decimate(10, iq[s, :n_done])
+        _, _, want, _ = po.fm_demodulate(dec)
+        a = np.concatenate([x for _, x in sorted(ps.audio[s], key=lambda t: t[0])])
+        assert a.shape == want.shape and np.abs(a - want).max() <= 1e-4
+        firsts = [f for f, _ in ps.spectra[s]]
+        assert firsts == sorted(firsts) and len(firsts) == n_done // batch      # delivered in order, once each
+    ps.close()
+
+
 def test_push_stream_payload_sink(pkg, cuda, po, synth):
     """What the reference sends its client: the 6-frame average at the start of every batch as payload bytes
     (cbb_main.c:48-59,121-130), computed on the device; the per-frame rows are neither computed nor copied."""
