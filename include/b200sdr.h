@@ -165,8 +165,11 @@ int b200_session_chain(b200_session* s, const uint8_t* h_iq, int64_t n_samples, 
  * into the stream's pinned host slot and returns; whenever a slot holds `batch_samples`
  * (a multiple of 5120, e.g. the reference's 204800-sample block, rf_decimator.c:65-66) it is
  * submitted asynchronously -- H2D copy, the fused chain kernel, history carry, D2H copies --
- * on one of the library's CUDA streams.  Finished batches are handed to the sinks from inside
- * push / poll / flush, on the calling thread, in order:
+ * on one of the library's CUDA streams.  Streams that run in step are submitted together: when every
+ * stream of a group of up to 16 consecutive streams has a full slot the group goes out as one copy and
+ * one launch; a stream that gets a whole batch ahead of its group goes out alone, and poll / flush submit
+ * whatever is waiting.  One producer thread per b200_stream (as the reference has one sensor thread).
+ * Finished batches are handed to the sinks from inside push / poll / flush, on the calling thread, in order:
  *   spectrum sink: n_frames rows of 1024 float dB (display order) starting at frame first_frame;
  *   audio sink:    n floats at fs/40 starting at audio sample first_sample.
  * The pointers passed to a sink are valid until it returns.  Batching is aligned to stream
@@ -189,7 +192,7 @@ typedef void (*b200_payload_sink)(void* user, int stream, int64_t first_frame, i
 int b200_stream_set_payload_sink(b200_stream* s, int K, b200_payload_sink sink);
 /* samples: len interleaved (re, im) byte pairs, i.e. a `const cmplx_u8*` */
 int b200_stream_push(b200_stream* s, int stream, const uint8_t* samples, int len);
-int b200_stream_poll(b200_stream* s);           /* deliver whatever has finished, never blocks */
+int b200_stream_poll(b200_stream* s);           /* submit what is waiting, deliver what has finished; never blocks */
 int b200_stream_flush(b200_stream* s);          /* wait for and deliver every submitted batch */
 int64_t b200_stream_pending_samples(const b200_stream* s, int stream);   /* buffered, not yet a whole batch */
 
