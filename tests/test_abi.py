@@ -62,3 +62,21 @@ def test_product_does_not_link_or_import_the_oracle():
                     f"{f} reaches for the oracle"
     blob = open(os.path.join(pkg_dir, "libb200sdr.so"), "rb").read()
     assert b"liboracle" not in blob and b"libref_rtlws" not in blob and b"orc_" not in blob
+
+
+def test_headers_are_plain_c_and_the_c_hosts_link(pkg, tmp_path):
+    """The reference is C: every header under include/ must compile as C99 on its own, and the C hosts of this repo
+    (examples/virtual_dongles.c, tools/push_bench.c) must compile and link against the two libraries -- no GPU needed."""
+    import subprocess
+    pkg.lib()
+    inc = os.path.join(ROOT, "include")
+    lib_dir = os.path.join(ROOT, "rtl-ws_b200")
+    for header in sorted(os.listdir(inc)):
+        src = tmp_path / (header + ".c")
+        src.write_text(f'#include "{header}"\nint main(void) {{ return 0; }}\n')
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + inc, "-c", str(src),
+                        "-o", str(tmp_path / (header + ".o"))], check=True)
+    for rel, libs in (("examples/virtual_dongles.c", ["-lb200sdr", "-lb200replay", "-lm"]),
+                      ("tools/push_bench.c", ["-lb200sdr"])):
+        subprocess.run(["gcc", "-O1", "-pthread", "-Wall", "-o", str(tmp_path / os.path.basename(rel)[:-2]),
+                        os.path.join(ROOT, rel), "-I" + inc, "-L" + lib_dir, "-Wl,-rpath," + lib_dir] + libs, check=True)
