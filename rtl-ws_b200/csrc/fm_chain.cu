@@ -154,7 +154,6 @@ __global__ void __launch_bounds__(FM_THREADS) fm_chain_kernel(const FmParams p, 
 constexpr int FW_T = 62;
 constexpr int FW_ND = 4 * FW_T + 32;              // 280 decimated samples, local index 0 <-> 4*n0 - 32
 constexpr int FW_NW = 2 * FW_T + 10;              // 134 first-stage outputs
-constexpr int FW_WARPS = 8;                       // per CTA: two per scheduler
 
 template <int R>
 struct FwCfg {
@@ -162,11 +161,14 @@ struct FwCfg {
     static constexpr int STAGE = FW_ND * SAMPLE_BYTES;            // 5600 bytes at R = 10
     static constexpr int WARP_SMEM = 2 * STAGE + 288 * 4 + 144 * 4 + 32;   // ring, demod[], work[], 2 mbarriers (+pad)
     static_assert(WARP_SMEM % 16 == 0, "TMA destinations must stay 16-byte aligned");
-    static constexpr int CTAS = (225 * 1024) / (FW_WARPS * WARP_SMEM + 1024) >= 2 ? 2 : 1;     // resident CTAs the compiler may plan for
+    // warps per CTA: as many as let TWO CTAs share an SM (8 at R <= 10: 16 warps per SM; 7 at R = 12; 5 at R = 16)
+    static constexpr int FIT = (113 * 1024) / WARP_SMEM;
+    static constexpr int WARPS = FIT > 8 ? 8 : (FIT < 4 ? 4 : FIT);
+    static constexpr int CTAS = 2;
 };
 
 template <int R>
-__global__ void __launch_bounds__(FW_WARPS * 32, FwCfg<R>::CTAS) fm_chain_warp_kernel(const FmParams p, const int tiles_per_stream)
+__global__ void __launch_bounds__(FwCfg<R>::WARPS * 32, FwCfg<R>::CTAS) fm_chain_warp_kernel(const FmParams p, const int tiles_per_stream)
 {
     using C = FwCfg<R>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -181,8 +183,8 @@ __global__ void __launch_bounds__(FW_WARPS * 32, FwCfg<R>::CTAS) fm_chain_warp_k
     const int64_t n_audio = p.n_samples / (4 * R);
     const uint32_t tps = (uint32_t) tiles_per_stream;
     const uint32_t total_tiles = (uint32_t) p.n_streams * tps;
-    const uint32_t gw = blockIdx.x * FW_WARPS + warp;
-    const uint32_t GW = gridDim.x * FW_WARPS;
+    const uint32_t gw = blockIdx.x * C::WARPS + warp;
+    const uint32_t GW = gridDim.x * C::WARPS;
     if (gw >= total_tiles) return;
     const uint32_t n_mine = (total_tiles - gw + GW - 1) / GW;
 
@@ -273,13 +275,13 @@ int launch_fm_warp(const FmParams& p, cudaStream_t stream)
         set_error("fm: batch too long");
         return B200_ERR_ARG;
     }
-    const int smem = FW_WARPS * C::WARP_SMEM;
+    const int smem = C::WARPS * C::WARP_SMEM;
     if (int rc = ensure_dynamic_smem((const void*) fm_chain_warp_kernel<R>, smem)) return rc;
-    const int per_sm = cached_occupancy((const void*) fm_chain_warp_kernel<R>, FW_WARPS * 32, smem);
+    const int per_sm = cached_occupancy((const void*) fm_chain_warp_kernel<R>, C::WARPS * 32, smem);
     int64_t grid = (int64_t) sm_count() * per_sm;
-    const int64_t needed = (total + FW_WARPS - 1) / FW_WARPS;
+    const int64_t needed = (total + C::WARPS - 1) / C::WARPS;
     if (grid > needed) grid = needed;
-    fm_chain_warp_kernel<R><<<(unsigned) grid, FW_WARPS * 32, smem, stream>>>(p, (int) tps);
+    fm_chain_warp_kernel<R><<<(unsigned) grid, C::WARPS * 32, smem, stream>>>(p, (int) tps);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
