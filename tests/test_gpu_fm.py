@@ -170,6 +170,32 @@ def test_chain_full_size_properties(pkg, cuda):
     assert audio.abs().max().item() <= 1.46404 ** 2 + 1e-6
 
 
+def test_fm_full_size_properties(pkg, cuda):
+    """BASELINE config 3 at its full size (2^30 samples of FM chain, R = 10) through properties:
+    (a) the CIC output is exact integer arithmetic: per stream, sum over decimated samples == sum over all bytes
+        - 128 per sample (int64 on the device);
+    (b) the standalone FM kernel and the fused chain kernel produce the same audio from the same bytes;
+    (c) |audio| is bounded by the limiter and the two half-bands."""
+    torch = cuda
+    n_streams, n = 256, 5120 * 820                     # 256 x 4 198 400 = 1.07e9 samples
+    assert n_streams * n >= 1 << 30
+    g = torch.Generator(device="cuda").manual_seed(11)
+    ring = pkg.StreamRing(n_streams, n)
+    ring.batch.copy_(torch.randint(0, 256, (n_streams, n, 2), dtype=torch.uint8, device="cuda", generator=g))
+    audio, dec = pkg.fm_exec(ring, decimated=True)
+    torch.cuda.synchronize()
+    want = torch.empty((n_streams, 2), dtype=torch.int64, device="cuda")
+    for s0 in range(0, n_streams, 32):
+        want[s0:s0 + 32] = ring.batch[s0:s0 + 32].to(torch.int32).sum(dim=1, dtype=torch.int64) - 128 * n
+    assert torch.equal(dec.sum(dim=1, dtype=torch.int64), want)
+    del dec
+    db = torch.empty((n_streams, n // 1024, 1024), dtype=torch.float32, device="cuda")
+    _, audio2 = pkg.chain_exec(ring, db=db)
+    torch.cuda.synchronize()
+    assert (audio - audio2).abs().max().item() <= 1e-6
+    assert audio.abs().max().item() <= 1.46404 ** 2 + 1e-6
+
+
 @pytest.mark.parametrize("n_streams,n_tiles", [(1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (2, 7), (3, 13), (1, 31), (5, 1)])
 def test_chain_pipeline_edges(pkg, cuda, po, synth, n_streams, n_tiles):
     """Few tiles per CTA / per group: ring prologue shorter than its depth, groups with no work,
