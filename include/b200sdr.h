@@ -120,6 +120,50 @@ int b200_fm_exec(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams
                  float* d_audio, int64_t audio_stride, int32_t* d_decimated, int64_t dec_stride,
                  void* cuda_stream);
 
+/* The same demodulator for DECIMATED input -- the signature of the reference's own callback,
+ * audio_fm_demodulator(const cmplx_s32*, int) (audio_main.h:12, audio_main.c:74-145), with its three
+ * function statics (audio_main.c:77-79) made explicit.  d_state: B200_FM_STATE_FLOATS floats per stream on
+ * the device, in/out: [0] previous phase, [1..10] delay_line_1, [11..20] delay_line_2, the rest is the
+ * library's; all zero = stream start.  d_decimated: [n_streams][dec_stride] cmplx_s32 (any int32 values:
+ * atan2_approx is evaluated in the reference's own order of operations); n_decimated a multiple of 4.
+ * Outputs: d_audio n_decimated / 4 floats per stream; optional d_demod (the limiter output of
+ * audio_main.c:114-130, n_decimated floats) and d_phase (atan2_approx itself), strides in floats.
+ * B200_FM_SKIP_STAGE2 reproduces a block that found the reference's pool full (audio_main.c:137): phase and
+ * first half-band advance, the second half-band and its delay line do not, d_audio is not written. */
+#define B200_FM_STATE_FLOATS 48
+#define B200_FM_SKIP_STAGE2 1
+int b200_fm_exec_cs32(const int32_t* d_decimated, int64_t dec_stride, int n_streams, int64_t n_decimated,
+                      float* d_state, float* d_audio, int64_t audio_stride, float* d_demod, int64_t demod_stride,
+                      float* d_phase, int64_t phase_stride, int flags, void* cuda_stream);
+/* Host-buffer form, the body of an rf_decimator_callback: one block of len cmplx_s32 from (borrowed) host
+ * memory in, len / 4 audio floats out; h_audio == NULL = B200_FM_SKIP_STAGE2; h_demod nullable.  The state
+ * lives in the handle; create = stream start.  libb200audio.so (include/rtlws_audio_compat.h) wraps this in
+ * the reference's audio_main.h interface. */
+typedef struct b200_fm_demod b200_fm_demod;
+b200_fm_demod* b200_fm_demod_create(void);
+void b200_fm_demod_destroy(b200_fm_demod* d);
+int b200_fm_demod_reset(b200_fm_demod* d);
+int b200_fm_demod_block(b200_fm_demod* d, const int32_t* h_signal, int len, float* h_audio, float* h_demod);
+
+/* ---- opt-in audio extensions: de-emphasis and 48 kHz output ----------------------------------
+ *
+ * NOT in the reference (its chain ends at fs / (4R) = 51.2 kS/s without de-emphasis, audio_main.c:133-139,
+ * while resources/rtl_ui.js:79-82 wants 48 kHz); off unless asked for, and with flags = 0 nothing changes.
+ *   B200_AUDIO_DEEMPH_50US / _75US  y[n] = y[n-1] + alpha (x[n] - y[n-1]), alpha = 1 - exp(-1 / (rate tau))
+ *   B200_AUDIO_RESAMPLE_48K         15/16 polyphase FIR (240-tap Blackman-windowed sinc, 16 taps per phase):
+ *                                   16 input samples -> 15 output samples; n_audio must be a multiple of 16
+ * De-emphasis runs first.  d_state: B200_AUDIO_POST_STATE_FLOATS floats per stream, in/out, zero = stream
+ * start.  d_out may not alias d_audio.  oracle/oracle.c restates both (orc_deemphasis, orc_resample_15_16). */
+#define B200_AUDIO_DEEMPH_50US 1
+#define B200_AUDIO_DEEMPH_75US 2
+#define B200_AUDIO_RESAMPLE_48K 4
+#define B200_AUDIO_POST_STATE_FLOATS 64
+int64_t b200_audio_post_out_samples(int64_t n_audio, int flags);
+int b200_audio_post(const float* d_audio, int64_t audio_stride, int n_streams, int64_t n_audio, double audio_rate_hz,
+                    int flags, float* d_state, float* d_out, int64_t out_stride, void* cuda_stream);
+/* the resampler's 240 prototype taps (host), for whoever wants to check them; returns 240 */
+int b200_audio_resample_taps(float* h240);
+
 /* ---- the full chain on the same IQ, read once ---------------------------------------------
  *
  * N = 1024 per-frame spectra (K = 1, hop = row_hop = 1024, rectangular: the reference's
@@ -246,6 +290,40 @@ int b200_wire_audio_messages(const float* d_audio, int64_t audio_stride, int n_s
 /* The lws_write calls of one audio message: fragment `index` (0..7) is `len` bytes at `offset` with `flags`. */
 int b200_wire_audio_fragment(int index, int32_t* offset, int32_t* len, int32_t* flags);
 int64_t b200_wire_reference_drain_index(int64_t wire_sample, int buffer_len);
+
+/* ---- multi-GPU: stream sharding and the one exchange --------------------------------------
+ *
+ * All DSP state of the reference is per stream (rf_decimator.c:23,28; audio_main.c:77-79), so streams shard
+ * across GPUs with nothing exchanged on the data path: global stream s belongs to rank s mod world, and a
+ * rank's streams are its local rows 0, 1, ... in that order (global id = rank + i * world).  The one
+ * collective gathers per-stream rows of equal size -- in practice the K-frame averaged payload bytes
+ * b200_chain_exec wrote to d_avg_u8, what main.c:80-84 sends a client -- to the rank that serves them.
+ * libnccl.so.2 is loaded on first use (NCCL 2.x; a single-GPU host never needs it).
+ *
+ *   one process per GPU:  rank 0 calls b200_comm_unique_id and hands the 128 bytes to the other ranks by
+ *                         whatever the host has (a file, a socket, MPI, torch.distributed); every rank then
+ *                         calls b200_comm_create on its own device;
+ *   one process, G GPUs:  b200_comm_create_all makes comms[i] for device i; b200_comm_gather_rows_all posts
+ *                         the exchange for all of them from one thread.
+ *
+ * b200_comm_gather_rows: d_send = this rank's local rows [b200_shard_count][row_bytes] (device, contiguous);
+ * on the root d_recv receives [n_streams_total][row_bytes] in GLOBAL stream order, other ranks pass NULL.
+ * Asynchronous on cuda_stream; row_bytes a multiple of 4.  world == 1 degenerates to a copy. */
+#define B200_COMM_ID_BYTES 128
+typedef struct b200_comm b200_comm;
+int b200_shard_count(int n_streams, int world, int rank);
+int b200_shard_stream(int n_streams, int world, int rank, int local_index);
+int b200_comm_unique_id(uint8_t* id128);
+b200_comm* b200_comm_create(const uint8_t* id128, int world, int rank);
+int b200_comm_create_all(int n_devices, b200_comm** comms);
+void b200_comm_destroy(b200_comm* c);
+int b200_comm_world(const b200_comm* c);
+int b200_comm_rank(const b200_comm* c);
+int b200_comm_nccl_version(void);       /* e.g. 22703; B200_ERR_CUDA if libnccl cannot be loaded */
+int b200_comm_gather_rows(b200_comm* c, const void* d_send, int n_streams_total, int row_bytes, void* d_recv,
+                          int root, void* cuda_stream);
+int b200_comm_gather_rows_all(b200_comm** comms, int n, const void* const* d_send, int n_streams_total, int row_bytes,
+                              void* d_recv, int root, void* const* cuda_streams);
 
 void* b200_host_alloc(uint64_t bytes);          /* pinned host memory */
 void b200_host_free(void* p);

@@ -420,3 +420,88 @@ int orc_chain_push(orc_chain* c, const uint8_t* iq, int len,
     }
     return 0;
 }
+
+/* ============ extensions that are NOT in the reference (product: csrc/audio_post.cu) ============
+ *
+ * The reference's chain ends at fs/(4R) = 51.2 kS/s without de-emphasis (audio_main.c:133-139,
+ * rf_decimator.c:65-66); its UI asks for a 48 kHz AudioContext (resources/rtl_ui.js:79-82).
+ * BASELINE.json's north star names "de-emphasis and resampler ... 48 kHz audio", so the product
+ * offers both as opt-in extensions.  There is no reference code to follow; what follows is the
+ * DEFINITION the product's kernels are checked against, written as the plain sequential loops. */
+
+/* single-pole de-emphasis: y[n] = y[n-1] + alpha * (x[n] - y[n-1]); *state = y[-1] in, y[n-1] out */
+void orc_deemphasis(const float* x, int n, float alpha, float* state, float* y)
+{
+    float prev = *state;
+    int i;
+    for (i = 0; i < n; ++i)
+    {
+        prev = prev + alpha * (x[i] - prev);
+        y[i] = prev;
+    }
+    *state = prev;
+}
+
+/* alpha = 1 - exp(-1 / (rate * tau)), evaluated in double and rounded once */
+float orc_deemphasis_alpha(double rate_hz, double tau_s)
+{
+    return (float) (1.0 - exp(-1.0 / (rate_hz * tau_s)));
+}
+
+/* the 15/16 resampler's prototype: 240-tap Blackman-windowed sinc, cutoff 1/32 cycles per
+ * interpolated sample (24 kHz at 15 * 51.2 kHz), scaled to a DC gain of 15 */
+void orc_resample_taps(float* h)
+{
+    const double pi = 3.14159265358979323846;
+    const double fc = 1.0 / 32.0;
+    const double mid = (ORC_RESAMPLE_TAPS - 1) / 2.0;
+    double w[ORC_RESAMPLE_TAPS];
+    double sum = 0.0;
+    int k;
+    for (k = 0; k < ORC_RESAMPLE_TAPS; ++k)
+    {
+        const double t = (double) k - mid;
+        const double a = 2.0 * pi * fc * t;
+        const double sinc = t == 0.0 ? 1.0 : sin(a) / a;
+        const double win = 0.42 - 0.5 * cos(2.0 * pi * (double) k / (ORC_RESAMPLE_TAPS - 1))
+                           + 0.08 * cos(4.0 * pi * (double) k / (ORC_RESAMPLE_TAPS - 1));
+        w[k] = sinc * win;
+        sum += w[k];
+    }
+    for (k = 0; k < ORC_RESAMPLE_TAPS; ++k)
+        h[k] = (float) (w[k] * 15.0 / sum);
+}
+
+/* y[m] = sum_{t=0}^{15} h[r + 15 t] * x[q - t], q = floor(16 m / 15), r = 16 m mod 15; x[-15..-1]
+ * comes from hist[0..14] (zero at stream start), which is then refreshed with the last 15 inputs.
+ * n must be a multiple of 16; writes n / 16 * 15 outputs. */
+int orc_resample_15_16(const float* x, int n, float* hist, float* y)
+{
+    float h[ORC_RESAMPLE_TAPS];
+    float ext[15];
+    int m, t, n_out;
+    if (n % 16 != 0)
+        return -1;
+    orc_resample_taps(h);
+    n_out = n / 16 * 15;
+    for (m = 0; m < n_out; ++m)
+    {
+        const int q = (16 * m) / 15;
+        const int r = 16 * m - 15 * q;
+        float acc = 0.0f;
+        for (t = 0; t < 16; ++t)
+        {
+            const int idx = q - t;
+            const float v = idx >= 0 ? x[idx] : hist[15 + idx];
+            acc += h[r + 15 * t] * v;
+        }
+        y[m] = acc;
+    }
+    for (t = 0; t < 15; ++t)
+    {
+        const int idx = n - 15 + t;
+        ext[t] = idx >= 0 ? x[idx] : hist[15 + idx];
+    }
+    memcpy(hist, ext, sizeof(ext));
+    return n_out;
+}

@@ -95,6 +95,13 @@ int orc_chain_push(orc_chain* c, const uint8_t* iq, int len,
                    int32_t* dec, int64_t* n_dec, int64_t dec_cap,
                    float* audio, int64_t* n_audio, int64_t audio_cap);
 
+/* ---- extensions without a reference counterpart (csrc/audio_post.cu); definitions, not ports ---- */
+#define ORC_RESAMPLE_TAPS 240
+void orc_deemphasis(const float* x, int n, float alpha, float* state, float* y);
+float orc_deemphasis_alpha(double rate_hz, double tau_s);
+void orc_resample_taps(float* h);
+int orc_resample_15_16(const float* x, int n, float* hist, float* y);
+
 #ifdef __cplusplus
 }
 #endif

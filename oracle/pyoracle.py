@@ -97,6 +97,11 @@ def port():
     lib.orc_chain_block_out.argtypes = [C.c_void_p]
     lib.orc_chain_push.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_int64,
                                    C.c_void_p, C.POINTER(C.c_int64), C.c_int64]
+    lib.orc_deemphasis.argtypes = [_f32p, C.c_int, C.c_float, _f32p, _f32p]
+    lib.orc_deemphasis_alpha.restype = C.c_float
+    lib.orc_deemphasis_alpha.argtypes = [C.c_double, C.c_double]
+    lib.orc_resample_taps.argtypes = [_f32p]
+    lib.orc_resample_15_16.argtypes = [_f32p, C.c_int, _f32p, _f32p]
     _port = lib
     return lib
 
@@ -223,6 +228,32 @@ def fm_demodulate(signal: np.ndarray, state: FmState | None = None):
     audio = np.empty(n // 4, dtype=np.float32)
     port().orc_fm_demodulate(signal, n, C.byref(st), demod, work, audio)
     return demod, work, audio, st
+
+
+def deemphasis(x: np.ndarray, rate_hz: float, tau_s: float, state: np.ndarray | None = None):
+    """Definition of the product's opt-in de-emphasis (not in the reference) -> (y, state[1])."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    st = np.zeros(1, np.float32) if state is None else state
+    y = np.empty_like(x)
+    port().orc_deemphasis(x, len(x), port().orc_deemphasis_alpha(rate_hz, tau_s), st, y)
+    return y, st
+
+
+def resample_taps() -> np.ndarray:
+    h = np.empty(240, dtype=np.float32)
+    port().orc_resample_taps(h)
+    return h
+
+
+def resample_15_16(x: np.ndarray, hist: np.ndarray | None = None):
+    """Definition of the product's opt-in 51.2 -> 48 kHz resampler (not in the reference) -> (y, hist[15])."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    h = np.zeros(15, np.float32) if hist is None else hist
+    y = np.empty(len(x) // 16 * 15, dtype=np.float32)
+    n = port().orc_resample_15_16(x, len(x), h, y)
+    if n < 0:
+        raise ValueError("resample_15_16 takes multiples of 16 samples")
+    return y, h
 
 
 class Chain:

@@ -33,6 +33,11 @@ EXPORTED_SYMBOLS = [
     "b200_wire_spectrum_header", "b200_wire_spectrum_message", "b200_wire_spectrum_messages",
     "b200_wire_audio_messages", "b200_wire_audio_fragment", "b200_wire_reference_drain_index",
     "b200_host_alloc", "b200_host_free",
+    "b200_fm_exec_cs32", "b200_fm_demod_create", "b200_fm_demod_destroy", "b200_fm_demod_reset", "b200_fm_demod_block",
+    "b200_audio_post", "b200_audio_post_out_samples", "b200_audio_resample_taps",
+    "b200_shard_count", "b200_shard_stream", "b200_comm_unique_id", "b200_comm_create", "b200_comm_create_all",
+    "b200_comm_destroy", "b200_comm_world", "b200_comm_rank", "b200_comm_nccl_version", "b200_comm_gather_rows",
+    "b200_comm_gather_rows_all",
     "spectrum_alloc", "spectrum_add_cmplx_u8", "spectrum_add_cmplx_s32", "spectrum_add_real_f32", "spectrum_free",
     "cic_decimate", "halfband_decimate",
     "rf_decimator_alloc", "rf_decimator_add_callback", "rf_decimator_set_parameters",
@@ -120,6 +125,28 @@ def lib() -> C.CDLL:
     L.b200_host_alloc.restype = vp
     L.b200_host_alloc.argtypes = [u64]
     L.b200_host_free.argtypes = [vp]
+    L.b200_fm_exec_cs32.argtypes = [vp, i64, i32, i64, vp, vp, i64, vp, i64, vp, i64, i32, vp]
+    L.b200_fm_demod_create.restype = vp
+    L.b200_fm_demod_destroy.restype = None
+    L.b200_fm_demod_destroy.argtypes = [vp]
+    L.b200_fm_demod_reset.argtypes = [vp]
+    L.b200_fm_demod_block.argtypes = [vp, vp, i32, vp, vp]
+    L.b200_audio_post.argtypes = [vp, i64, i32, i64, C.c_double, i32, vp, vp, i64, vp]
+    L.b200_audio_post_out_samples.restype = i64
+    L.b200_audio_post_out_samples.argtypes = [i64, i32]
+    L.b200_audio_resample_taps.argtypes = [vp]
+    L.b200_shard_count.argtypes = [i32, i32, i32]
+    L.b200_shard_stream.argtypes = [i32, i32, i32, i32]
+    L.b200_comm_unique_id.argtypes = [vp]
+    L.b200_comm_create.restype = vp
+    L.b200_comm_create.argtypes = [vp, i32, i32]
+    L.b200_comm_create_all.argtypes = [i32, C.POINTER(vp)]
+    L.b200_comm_destroy.restype = None
+    L.b200_comm_destroy.argtypes = [vp]
+    L.b200_comm_world.argtypes = [vp]
+    L.b200_comm_rank.argtypes = [vp]
+    L.b200_comm_gather_rows.argtypes = [vp, vp, i32, i32, vp, i32, vp]
+    L.b200_comm_gather_rows_all.argtypes = [C.POINTER(vp), i32, C.POINTER(vp), i32, i32, vp, i32, C.POINTER(vp)]
     # reference-named interface
     L.spectrum_alloc.restype = vp
     L.spectrum_alloc.argtypes = [i32]
@@ -314,6 +341,133 @@ def chain_exec(ring: StreamRing, gain_db: int = 0, db=None, audio=None, avg_u8=N
                                    audio.stride(0), C.c_void_p(avg_u8.data_ptr()) if avg_u8 is not None else None,
                                    K_avg, _stream_ptr(stream)), "b200_chain_exec_r")
     return db, audio
+
+
+FM_STATE_FLOATS = 48
+FM_SKIP_STAGE2 = 1
+AUDIO_DEEMPH_50US, AUDIO_DEEMPH_75US, AUDIO_RESAMPLE_48K = 1, 2, 4
+AUDIO_POST_STATE_FLOATS = 64
+COMM_ID_BYTES = 128
+
+
+def fm_exec_cs32(dec, state, audio=None, demod: bool = False, phase: bool = False, flags: int = 0, stream=None):
+    """b200_fm_exec_cs32: decimated cmplx_s32 [n_streams, n, 2] (cuda int32) + carried state
+    [n_streams, FM_STATE_FLOATS] -> dict(audio, demod?, phase?).  audio_main.c:110-139."""
+    torch = _torch()
+    assert dec.is_cuda and dec.dtype == torch.int32 and dec.dim() == 3 and dec.shape[2] == 2 and dec.stride(1) == 2
+    assert state.is_cuda and state.dtype == torch.float32 and state.shape == (dec.shape[0], FM_STATE_FLOATS)
+    n_streams, n = dec.shape[0], dec.shape[1]
+    res = {}
+    skip = bool(flags & FM_SKIP_STAGE2)
+    if not skip:
+        res["audio"] = audio if audio is not None else torch.empty((n_streams, n // 4), dtype=torch.float32, device=dec.device)
+    if demod:
+        res["demod"] = torch.empty((n_streams, n), dtype=torch.float32, device=dec.device)
+    if phase:
+        res["phase"] = torch.empty((n_streams, n), dtype=torch.float32, device=dec.device)
+    ptr = lambda k: C.c_void_p(res[k].data_ptr()) if k in res else None
+    stride = lambda k: res[k].stride(0) if k in res else 0
+    _check(lib().b200_fm_exec_cs32(C.c_void_p(dec.data_ptr()), dec.stride(0) // 2, n_streams, n,
+                                   C.c_void_p(state.data_ptr()), ptr("audio"), stride("audio"), ptr("demod"),
+                                   stride("demod"), ptr("phase"), stride("phase"), flags, _stream_ptr(stream)),
+           "b200_fm_exec_cs32")
+    return res
+
+
+class FmDemod:
+    """b200_fm_demod_*: the body of an rf_decimator_callback -- host cmplx_s32 blocks in, host audio out."""
+
+    def __init__(self):
+        _torch()
+        self.h = lib().b200_fm_demod_create()
+        if not self.h:
+            raise B200Error(f"b200_fm_demod_create: {last_error()}")
+
+    def block(self, signal: np.ndarray, want_audio: bool = True, want_demod: bool = False):
+        signal = np.ascontiguousarray(signal, dtype=np.int32).reshape(-1, 2)
+        n = len(signal)
+        audio = np.empty(n // 4, dtype=np.float32) if want_audio else None
+        demod = np.empty(n, dtype=np.float32) if want_demod else None
+        _check(lib().b200_fm_demod_block(self.h, signal.ctypes.data, n, audio.ctypes.data if want_audio else None,
+                                         demod.ctypes.data if want_demod else None), "b200_fm_demod_block")
+        return audio, demod
+
+    def reset(self):
+        _check(lib().b200_fm_demod_reset(self.h), "b200_fm_demod_reset")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_fm_demod_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def audio_post(audio, state, flags: int, rate_hz: float = 51200.0, out=None, stream=None):
+    """b200_audio_post: opt-in de-emphasis / 15:16 resampling of [n_streams, n] f32 audio rows (extensions,
+    not in the reference).  state: cuda float32 [n_streams, AUDIO_POST_STATE_FLOATS], zero = stream start."""
+    torch = _torch()
+    assert audio.is_cuda and audio.dtype == torch.float32 and audio.dim() == 2 and audio.stride(1) == 1
+    n_streams, n = audio.shape
+    n_out = int(lib().b200_audio_post_out_samples(n, flags))
+    if n_out < 0:
+        raise B200Error("audio_post: the resampler takes multiples of 16 samples")
+    if out is None:
+        out = torch.empty((n_streams, n_out), dtype=torch.float32, device=audio.device)
+    _check(lib().b200_audio_post(C.c_void_p(audio.data_ptr()), audio.stride(0), n_streams, n, rate_hz, flags,
+                                 C.c_void_p(state.data_ptr()), C.c_void_p(out.data_ptr()), out.stride(0),
+                                 _stream_ptr(stream)), "b200_audio_post")
+    return out
+
+
+def resample_taps() -> np.ndarray:
+    h = np.empty(240, dtype=np.float32)
+    assert lib().b200_audio_resample_taps(h.ctypes.data) == 240
+    return h
+
+
+class Comm:
+    """b200_comm_*: the NCCL communicator behind the one exchange of the path (gather of per-stream rows).
+    One process per GPU: `Comm.unique_id()` on rank 0, distribute the 128 bytes, `Comm(id, world, rank)`."""
+
+    def __init__(self, id128: bytes, world: int, rank: int):
+        _torch()
+        assert len(id128) == COMM_ID_BYTES
+        self.world, self.rank = world, rank
+        buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(id128)
+        self.h = lib().b200_comm_create(buf, world, rank)
+        if not self.h:
+            raise B200Error(f"b200_comm_create: {last_error()}")
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_ubyte * COMM_ID_BYTES)()
+        _check(lib().b200_comm_unique_id(buf), "b200_comm_unique_id")
+        return bytes(buf)
+
+    def gather_rows(self, send, n_streams_total: int, recv=None, root: int = 0, stream=None):
+        """send: cuda tensor [n_local, row...] (contiguous); recv (root): [n_streams_total, row...]."""
+        row_bytes = int(send[0].numel() * send.element_size()) if send.shape[0] else int(recv[0].numel() * recv.element_size())
+        _check(lib().b200_comm_gather_rows(self.h, C.c_void_p(send.data_ptr()), n_streams_total, row_bytes,
+                                           C.c_void_p(recv.data_ptr()) if recv is not None else None, root,
+                                           _stream_ptr(stream)), "b200_comm_gather_rows")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_comm_destroy(self.h)
+            self.h = None
+
+
+def shard_count(n_streams: int, world: int, rank: int) -> int:
+    return int(lib().b200_shard_count(n_streams, world, rank))
+
+
+def shard_stream(n_streams: int, world: int, rank: int, i: int) -> int:
+    return int(lib().b200_shard_stream(n_streams, world, rank, i))
 
 
 class Session:

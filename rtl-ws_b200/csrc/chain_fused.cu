@@ -18,6 +18,8 @@
 // All 12 warps an SM holds (two CTAs at <= 168 registers) are transform-capable; none idles
 // on a role.  Tiles are independent (a tile's audio depends on input bytes only, through the
 // history), so CTAs stride over (stream, tile) with no inter-CTA communication.
+#include <stdlib.h>
+
 #include "b200_common.cuh"
 #include "fft1024_warp.cuh"
 #include "fm_kernels.cuh"
@@ -52,6 +54,8 @@ struct ChainParams {
     float* audio;                  // [n_streams][tiles_per_stream * 128], row stride audio_stride
     int64_t audio_stride;
     float dboff;                   // 10*log10(g) + FFT1024_DB_SHIFT
+    uint32_t tps_magic;            // tile / tiles_per_stream = (tile * tps_magic) >> tps_shift for tile < 2^31
+    int tps_shift;
     const float2* twiddle;
 };
 
@@ -195,6 +199,198 @@ __global__ void __launch_bounds__(CF_THREADS, 1) chain_fused_kernel(const ChainP
     if (n_mine > 0 && warp == service) audio_job(n_mine - 1);
 }
 
+// ---- the job-queue form ----------------------------------------------------------------------
+// Same tile, same ring, same barriers, same arithmetic as chain_fused_kernel, but the six jobs of
+// a tile (service + five frames) are no longer tied to six particular warps: every warp of a group
+// takes the next job from a shared counter.  That decouples the warp count from the tile shape, so
+// a group can be 8 warps (two groups) or 16 (one group) per SM -- four warps per scheduler
+// instead of three -- and a warp that drew the short service job simply comes back sooner.  Jobs
+// are claimed in order and only ever wait for lower-numbered jobs (ring refills, demod hand-off), so
+// the lowest unfinished job can always run: no deadlock whatever the interleaving.
+// With TWS the inter-pass twiddles W_1024^(n2 k1) come from a shared [n2][k1] table (8 KB per
+// CTA, one LDS.64 per pair member, conflict-free) instead of 62 registers per lane; that is what
+// lets 16 warps fit at 128 registers.
+template <int W, int G, int S, int D, bool TWS>
+struct ChainJobsCfg {
+    static constexpr int THREADS = W * G * 32;
+    static constexpr int RING_BYTES = S * CF_STAGE_BYTES;
+    static constexpr int XCH_BYTES = W * FFT1024_XCH_BYTES;
+    static constexpr int DEMOD_BYTES = D * CF_ND_PAD * 4;
+    static constexpr int WORK_BYTES = D * CF_WORK * 4;
+    static constexpr int BAR_BYTES = (2 * S + 2 * D) * 8 + 8;          // + the job counter
+    static constexpr int GROUP_SMEM = (RING_BYTES + XCH_BYTES + DEMOD_BYTES + WORK_BYTES + BAR_BYTES + 127) / 128 * 128;
+    static constexpr int TW_BYTES = TWS ? 32 * 32 * 8 : 0;
+    static constexpr int SMEM = G * GROUP_SMEM + TW_BYTES;
+    static_assert(SMEM <= 232448, "more shared memory than a CTA may have on sm_100");
+    static_assert(CF_STAGE_BYTES % 128 == 0, "ring stages must stay 128-byte aligned");
+};
+
+template <int W, int G, int S, int D, bool TWS>
+__global__ void __launch_bounds__(W * G * 32, 1) chain_jobs_kernel(const ChainParams p)
+{
+    using C = ChainJobsCfg<W, G, S, D, TWS>;
+    extern __shared__ __align__(128) uint8_t smem_all[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int group = (tid >> 5) / W;
+    const int warp = (tid >> 5) % W;
+    uint8_t* smem = smem_all + group * C::GROUP_SMEM;
+    uint8_t* ring = smem;
+    float2* xch = reinterpret_cast<float2*>(smem + C::RING_BYTES + warp * FFT1024_XCH_BYTES);
+    float* demod_base = reinterpret_cast<float*>(smem + C::RING_BYTES + C::XCH_BYTES);       // [D][CF_ND_PAD]
+    float* work_base = demod_base + D * CF_ND_PAD;                                            // [D][CF_WORK]
+    uint64_t* full = reinterpret_cast<uint64_t*>(work_base + D * CF_WORK);
+    uint64_t* empty = full + S;
+    uint64_t* demod_full = empty + S;
+    uint64_t* demod_empty = demod_full + D;
+    uint32_t* next_job = reinterpret_cast<uint32_t*>(demod_empty + D);
+    const float2* tws = reinterpret_cast<const float2*>(smem_all + G * C::GROUP_SMEM);      // [n2][k1]
+
+    const uint32_t total_tiles = (uint32_t) p.n_streams * (uint32_t) p.tiles_per_stream;
+    const uint32_t first = blockIdx.x * G + group;
+    const uint32_t stride = gridDim.x * G;
+    const uint32_t n_mine = first < total_tiles ? (total_tiles - first + stride - 1) / stride : 0;
+
+    // tile -> (stream, tile in stream) without a division: tile * magic >> shift (exact below 2^31)
+    auto locate = [&](uint32_t tile, uint32_t& s, uint32_t& t) {
+        s = (uint32_t) (((uint64_t) tile * p.tps_magic) >> p.tps_shift);
+        t = tile - s * (uint32_t) p.tiles_per_stream;
+    };
+    auto issue = [&](uint32_t it) {
+        uint32_t s, t;
+        locate(first + it * stride, s, t);
+        const int st = it % S;
+        const uint8_t* src = p.iq + (int64_t) s * p.stream_stride_bytes + 2 * ((int64_t) t * CF_TILE - CF_HIST);
+        mbar_arrive_expect_tx(&full[st], CF_STAGE_BYTES);
+        tma_load_1d(ring + st * CF_STAGE_BYTES, src, CF_STAGE_BYTES, &full[st]);
+    };
+    // the two half-band decimators of local tile `it` (audio_main.c:133,139); one warp
+    auto audio_job = [&](uint32_t it) {
+        uint32_t s, t;
+        locate(first + it * stride, s, t);
+        const int buf = it % D;
+        const float* demod = demod_base + buf * CF_ND_PAD;
+        float* work = work_base + buf * CF_WORK;
+        mbar_wait(&demod_full[buf], (it / D) & 1);
+        for (int m = lane; m < CF_NW; m += 32)              // work index 0 <-> 2*n0 - 10
+            work[m] = halfband_from(demod + 2 * m + 2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&demod_empty[buf]);
+        float* out = p.audio + (int64_t) s * p.audio_stride + (int64_t) t * 128;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) out[32 * r + lane] = halfband_from(work + 2 * (32 * r + lane));
+    };
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 6);
+        }
+        for (int i = 0; i < D; ++i) {
+            mbar_init(&demod_full[i], 6);
+            mbar_init(&demod_empty[i], 1);
+        }
+        *next_job = 0;
+        fence_mbar_init();
+        for (uint32_t it = 0; it < S - 1 && it < n_mine; ++it) issue(it);
+    }
+    if (TWS) {
+        float2* t = const_cast<float2*>(tws);
+        for (int i = tid; i < 1024; i += C::THREADS) t[i] = __ldg(&p.twiddle[((i >> 5) * (i & 31)) & 1023]);
+    }
+    __syncthreads();
+
+    float2 tw[32];
+    if (!TWS) fft1024_load_twiddles(p.twiddle, lane, tw);
+
+    // jobs 6*it + pos: pos 0 = the tile's service job, 1..5 = frames 0..4; job 6*n_mine = the last tile's audio
+    const uint32_t n_jobs = n_mine > 0 ? 6 * n_mine + 1 : 0;
+    for (;;) {
+        uint32_t job = 0;
+        if (lane == 0) job = atomicAdd(next_job, 1u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= n_jobs) break;
+        const uint32_t it = job / 6;
+        const int pos = (int) (job - 6 * it);
+        if (it == n_mine) {
+            audio_job(n_mine - 1);
+            break;
+        }
+        const int st = it % S;
+        const int buf = it % D;
+        float* demod = demod_base + buf * CF_ND_PAD;
+
+        mbar_wait(&full[st], (it / S) & 1);
+        const uint8_t* in = ring + st * CF_STAGE_BYTES;
+
+        // ---- discriminator share: 3 of the tile's 18 chunks of 31 outputs (lane 0 only supplies
+        //      phase[j-1]); demod[buf] must have been drained by the audio job of tile it - D ----
+        if (it >= (uint32_t) D) mbar_wait(&demod_empty[buf], ((it / D) - 1) & 1);
+#pragma unroll
+        for (int c3 = 0; c3 < 3; ++c3) {
+            const int j = 31 * (pos + 6 * c3) + lane;
+            // the last chunk's lanes 17..31 read up to 280 bytes past the stage -- still inside this
+            // group's shared memory -- and write demod[544..557], padding that is never read
+            uint32_t ure, uim;
+            cic10_sum(reinterpret_cast<const uint32_t*>(in + j * 20), ure, uim);
+            const float ph = atan2_approx_dev2(__uint_as_float(uim) - CIC_MAGIC, __uint_as_float(ure) - CIC_MAGIC);
+            const float prev = __shfl_up_sync(0xffffffffu, ph, 1);
+            if (lane > 0) demod[j] = fm_limit(ph, prev);                   // demod[0] is never read
+        }
+
+        if (pos > 0) {
+            const int slot = pos - 1;
+            c64 a[32];
+            fft1024_load<false>(reinterpret_cast<const uint16_t*>(in + 2 * CF_HIST + 2048 * slot), nullptr, lane, a);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty[st]);
+                mbar_arrive(&demod_full[buf]);
+            }
+            fft1024_pass1<true>(a);
+            c64 b[32];
+            if (TWS)
+                fft1024_pass2_smem_tw<false>(a, tws + lane, xch, lane, b);
+            else
+                fft1024_pass2(a, tw, xch, lane, b);
+            float pw[32];
+            fft1024_power(b, pw);
+            // DC-position patch (spectrum.c:30-33): display index 512 takes display index 511's value
+            const float left = __shfl_sync(0xffffffffu, pw[31], 31);
+            if (lane == 0) pw[0] = left;
+            // rows of all streams are contiguous: row = 5 * tile + frame
+            fft1024_store_db(p.db + ((size_t) (first + it * stride) * 5 + slot) * 1024 + lane, pw, p.dboff);
+        } else {
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty[st]);
+                mbar_arrive(&demod_full[buf]);
+                // keep the ring full: tile it + S - 1 goes into the stage tile it - 1 used
+                if (it + S - 1 < n_mine) {
+                    if (it > 0) mbar_wait(&empty[(it - 1) % S], ((it - 1) / S) & 1);
+                    issue(it + S - 1);
+                }
+            }
+            __syncwarp();
+            if (it > 0) audio_job(it - 1);
+        }
+    }
+}
+
+template <int W, int G, int S, int D, bool TWS>
+int launch_chain_jobs(const ChainParams& p, int64_t total, cudaStream_t stream)
+{
+    using C = ChainJobsCfg<W, G, S, D, TWS>;
+    auto kern = chain_jobs_kernel<W, G, S, D, TWS>;
+    if (int rc = ensure_dynamic_smem((const void*) kern, C::SMEM)) return rc;
+    int64_t grid = sm_count();
+    const int64_t needed = (total + G - 1) / G;
+    if (grid > needed) grid = needed;
+    kern<<<(unsigned) grid, C::THREADS, C::SMEM, stream>>>(p);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
 }  // namespace
 
 int launch_chain_fused(const uint8_t* d_iq, int64_t stride, int n_streams, int64_t n_samples, float db_offset,
@@ -218,6 +414,24 @@ int launch_chain_fused(const uint8_t* d_iq, int64_t stride, int n_streams, int64
     // the plan's offset is 10*log10(g / (K * 2^14)) with K = 1; the fused unpack carries 2^30
     p.dboff = db_offset - 16.0f * DB_PER_LOG2;
     p.twiddle = twiddle;
+    // tile / tiles_per_stream by multiplication: L = ceil(log2 d), magic = ceil(2^(31+L) / d) fits 32 bits and is
+    // exact for every tile < 2^31 (the error magic * d - 2^(31+L) is below d <= 2^L)
+    int L = 0;
+    while ((1ll << L) < tiles_per_stream) ++L;
+    p.tps_magic = (uint32_t) (((1ull << (31 + L)) + (uint64_t) tiles_per_stream - 1) / (uint64_t) tiles_per_stream);
+    p.tps_shift = 31 + L;
+    const char* venv = getenv("B200_CHAIN_VARIANT");       // tuning knob while the variants are being measured
+    const int variant = venv ? atoi(venv) : 6;
+    switch (variant) {
+        case 1: return launch_chain_jobs<16, 1, 5, 5, true>(p, total, stream);
+        case 2: return launch_chain_jobs<8, 2, 3, 2, true>(p, total, stream);
+        case 3: return launch_chain_jobs<6, 2, 4, 4, false>(p, total, stream);
+        case 4: return launch_chain_jobs<6, 2, 4, 4, true>(p, total, stream);
+        case 5: return launch_chain_jobs<14, 1, 5, 5, true>(p, total, stream);
+        case 6: return launch_chain_jobs<18, 1, 4, 4, true>(p, total, stream);
+        case 7: return launch_chain_jobs<20, 1, 3, 4, true>(p, total, stream);
+        default: break;
+    }
     if (int rc = ensure_dynamic_smem((const void*) chain_fused_kernel, CF_SMEM)) return rc;
     const int ctas_per_sm = cached_occupancy((const void*) chain_fused_kernel, CF_THREADS, CF_SMEM);
     int64_t grid = (int64_t) sm_count() * ctas_per_sm;

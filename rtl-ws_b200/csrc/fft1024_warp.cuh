@@ -73,8 +73,14 @@ __device__ __forceinline__ void fft1024_pass1(c64 (&a)[32])
 __device__ __forceinline__ void fft1024_pass2(c64 (&a)[32], const float2 (&tw)[32], float2* xch, int lane, c64 (&b)[32])
 {
     __syncwarp();           // every lane is done reading xch for the previous frame
+    // stored as float2 halves on purpose: a 64-bit store of the packed register makes ptxas copy every
+    // value that was also unpacked (the "2u - s" butterflies) into a scratch pair first -- 38 MOVs per frame
 #pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) reinterpret_cast<c64*>(xch)[k1 * FFT1024_XCH_STRIDE + lane] = a[k1];
+    for (int k1 = 0; k1 < 32; ++k1) {
+        float re, im;
+        cunpack(a[k1], re, im);
+        xch[k1 * FFT1024_XCH_STRIDE + lane] = make_float2(re, im);
+    }
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
@@ -112,6 +118,53 @@ __device__ __forceinline__ void fft1024_core(c64 (&a)[32], const float2 (&tw)[32
 __host__ __device__ constexpr int fft1024_col(int k2)
 {
     return 32 * ((k2 + 16) & 31);
+}
+
+// pass 2 with the inter-pass twiddles in a shared [n2][k1] table (tws_lane = table + lane)
+template <bool SYNC_BEFORE>
+__device__ __forceinline__ void fft1024_pass2_smem_tw(c64 (&a)[32], const float2* tws_lane, float2* xch, int lane,
+                                                      c64 (&b)[32])
+{
+    if (SYNC_BEFORE) __syncwarp();
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+        float re, im;
+        cunpack(a[k1], re, im);
+        xch[k1 * FFT1024_XCH_STRIDE + lane] = make_float2(re, im);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&xch[lane * FFT1024_XCH_STRIDE + 2 * m]);
+        b[bitrev<32>(2 * m)] = v.x;
+        b[bitrev<32>(2 * m + 1)] = v.y;
+    }
+    fft_dit32_pretwiddled_smem(b, tws_lane);
+}
+
+// |X|^2 of the transform's output, as raw power (see FFT1024_POWER_SCALE)
+__device__ __forceinline__ void fft1024_power(const c64 (&b)[32], float (&pw)[32])
+{
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) {
+        float re, im;
+        cunpack(b[k2], re, im);
+        pw[k2] = fmaf(re, re, im * im);
+    }
+}
+
+// dB rows (cbb_main.c:125 without the truncation): 10*log10(pw) + dboff for two bins per packed FMA
+__device__ __forceinline__ void fft1024_store_db(float* out_lane, const float (&pw)[32], float dboff)
+{
+    const c64 scale = cpack(DB_PER_LOG2, DB_PER_LOG2);
+    const c64 off = cpack(dboff, dboff);
+#pragma unroll
+    for (int k2 = 0; k2 < 32; k2 += 2) {
+        float d0, d1;
+        cunpack(cfma2(cpack(lg2_ftz(pw[k2]), lg2_ftz(pw[k2 + 1])), scale, off), d0, d1);
+        __stcs(out_lane + fft1024_col(k2), d0);
+        __stcs(out_lane + fft1024_col(k2 + 1), d1);
+    }
 }
 
 }  // namespace b200

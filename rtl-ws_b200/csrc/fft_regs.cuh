@@ -59,6 +59,15 @@ __device__ __forceinline__ c64 cfma2(c64 a, c64 b, c64 c)   // lane-wise a * b +
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
+// Store a packed complex number.  Written as two float halves on purpose: with a 64-bit store of the
+// packed register ptxas first copies every value that was also unpacked somewhere (the "2u - s" form of
+// the butterflies unpacks s) into a scratch register pair -- one MOV pair per stored value.
+__device__ __forceinline__ void cstore(c64* dst, c64 v)
+{
+    float re, im;
+    cunpack(v, re, im);
+    *reinterpret_cast<float2*>(dst) = make_float2(re, im);
+}
 // general complex product a * w with w = (wr, wi):  (ar*wr - ai*wi, ai*wr + ar*wi)
 //   = a * (wr, wr) + (-ai, ar) * (wi, wi)
 __device__ __forceinline__ c64 cmul(c64 a, float wr, float wi)
@@ -196,6 +205,30 @@ __device__ __forceinline__ void fft_dit32(c64 (&a)[32], const float2 (&tw)[32])
         } else {
             dit_butterfly(a[g], a[g + 1], 0);
         }
+    }
+#pragma unroll
+    for (int half = 2; half <= 16; half <<= 1) {
+#pragma unroll
+        for (int g = 0; g < 32; g += 2 * half) {
+#pragma unroll
+            for (int k = 0; k < half; ++k) dit_butterfly(a[g + k], a[g + k + half], k * (16 / half));
+        }
+    }
+}
+
+// The same 32-point transform with the pre-multipliers read just in time from shared memory:
+// x[n] is multiplied by twp[32 * n] (n = 0 taken as 1).  twp already points at this lane's column
+// of a [32][32] table, so a warp load is 256 contiguous bytes.  Frees the 62 registers a
+// lane-private copy costs (chain_fused.cu runs 16 warps per SM at 128 registers with it).
+__device__ __forceinline__ void fft_dit32_pretwiddled_smem(c64 (&a)[32], const float2* twp)
+{
+#pragma unroll
+    for (int g = 0; g < 32; g += 2) {
+        const int na = bitrev<32>(g);
+        const int nb = bitrev<32>(g + 1);
+        const float2 ta = na == 0 ? make_float2(1.0f, 0.0f) : twp[32 * na];
+        const float2 tb = twp[32 * nb];
+        dit_butterfly_pretwiddled(a[g], a[g + 1], na == 0, ta, tb);
     }
 #pragma unroll
     for (int half = 2; half <= 16; half <<= 1) {

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(S2K_THREADS, 1) spectrum2048_kernel(const Spec
 
             __syncwarp();                                     // every lane has read its rows of the previous frame
 #pragma unroll
-            for (int k1 = 0; k1 < 64; ++k1) tile[k1 * 32 + tile_col2k(k1, lane)] = a[k1];
+            for (int k1 = 0; k1 < 64; ++k1) cstore(&tile[k1 * 32 + tile_col2k(k1, lane)], a[k1]);
             __syncwarp();
 
             // ---- pass 2: rows k1 = lane and lane + 32 ----

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(S4K_THREADS, 1) spectrum4096_kernel(const Spec
 
             if (f > 0) mbar_wait(tdone, (f - 1) & 1);         // both warps hold their rows of frame f - 1
 #pragma unroll
-            for (int k1 = 0; k1 < 64; ++k1) tile[k1 * 64 + tile_col(k1, t)] = a[k1];
+            for (int k1 = 0; k1 < 64; ++k1) cstore(&tile[k1 * 64 + tile_col(k1, t)], a[k1]);
             __syncwarp();
             if (lane == 0) mbar_arrive(tfull);
             mbar_wait(tfull, f & 1);

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(MxCfg<M>::THREADS, MxCfg<M>::CTAS_PER_SM) spec
                     const float2 w = __ldg(twr + 32 * k2);
                     z = cmul(z, w.x, w.y);
                 }
-                reinterpret_cast<c64*>(xch)[k2 * 32 + lane] = z;
+                cstore(&reinterpret_cast<c64*>(xch)[k2 * 32 + lane], z);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&zfull[set]);
