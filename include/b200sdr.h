@@ -145,6 +145,12 @@ void b200_fm_demod_destroy(b200_fm_demod* d);
 int b200_fm_demod_reset(b200_fm_demod* d);
 int b200_fm_demod_block(b200_fm_demod* d, const int32_t* h_signal, int len, float* h_audio, float* h_demod);
 
+/* Diagnostic: atan2_approx (common_sp.h:40-76) as each kernel family evaluates it, on n integer pairs
+ * (y, x) -> n floats.  which = 0: the single-quotient form of the FM kernels (|v| < 4096), 1: the folded form
+ * of the fused chain kernel, 2: the reference's own order of operations (b200_fm_exec_cs32).  Tests pin all
+ * three to the reference's grid. */
+int b200_debug_atan2(const int32_t* d_yx, int n, float* d_out, int which, void* cuda_stream);
+
 /* ---- opt-in audio extensions: de-emphasis and 48 kHz output ----------------------------------
  *
  * NOT in the reference (its chain ends at fs / (4R) = 51.2 kS/s without de-emphasis, audio_main.c:133-139,
@@ -153,7 +159,7 @@ int b200_fm_demod_block(b200_fm_demod* d, const int32_t* h_signal, int len, floa
  *   B200_AUDIO_RESAMPLE_48K         15/16 polyphase FIR (240-tap Blackman-windowed sinc, 16 taps per phase):
  *                                   16 input samples -> 15 output samples; n_audio must be a multiple of 16
  * De-emphasis runs first.  d_state: B200_AUDIO_POST_STATE_FLOATS floats per stream, in/out, zero = stream
- * start.  d_out may not alias d_audio.  oracle/oracle.c restates both (orc_deemphasis, orc_resample_15_16). */
+ * start.  d_out may not alias d_audio.  The test oracle restates both as plain sequential loops. */
 #define B200_AUDIO_DEEMPH_50US 1
 #define B200_AUDIO_DEEMPH_75US 2
 #define B200_AUDIO_RESAMPLE_48K 4
@@ -324,6 +330,17 @@ int b200_comm_gather_rows(b200_comm* c, const void* d_send, int n_streams_total,
                           int root, void* cuda_stream);
 int b200_comm_gather_rows_all(b200_comm** comms, int n, const void* const* d_send, int n_streams_total, int row_bytes,
                               void* d_recv, int root, void* const* cuda_streams);
+
+/* One process, G GPUs, HOST buffers: the session above once per device behind one object.  Arrays are in
+ * GLOBAL stream order, [n_streams][...]; stream s runs on device s mod n_gpus (its rows are read and
+ * written in place with a pitch of n_gpus rows), all devices run concurrently, and h_avg_u8 (nullable;
+ * needs K_avg >= 1 at create) receives the K_avg-frame averaged payload bytes of every stream,
+ * [n_streams][1024], gathered on device 0 over NCCL first.  R = 10, n_samples a multiple of 5120. */
+typedef struct b200_multi b200_multi;
+b200_multi* b200_multi_create(int n_gpus, int n_streams, int64_t max_samples_per_batch, int gain_db, int K_avg);
+void b200_multi_destroy(b200_multi* m);
+int b200_multi_chain(b200_multi* m, const uint8_t* h_iq, int64_t n_samples, float* h_db, float* h_audio,
+                     uint8_t* h_avg_u8);
 
 void* b200_host_alloc(uint64_t bytes);          /* pinned host memory */
 void b200_host_free(void* p);

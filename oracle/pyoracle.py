@@ -26,6 +26,7 @@ REF_BENCH = os.path.join(HERE, "_ref", "ref_bench")
 # the reference's own glue (cbb_main.c, audio_main.c, signal_source.c) linked against the PRODUCT
 # library instead of the reference's spectrum.o / resample.o / rf_decimator.o
 DROPIN_SO = os.path.join(HERE, "_ref", "libdropin_rtlws.so")
+DROPIN_AUDIO_SO = os.path.join(HERE, "_ref", "libdropin_audio_rtlws.so")   # ... and audio_main.o replaced by libb200audio.so
 REPLAY_SO = os.path.join(HERE, "_ref", "libreplay_rtlws.so")     # reference signal_source.c over libb200replay.so
 PRODUCT_SO = os.path.join(os.path.dirname(HERE), "rtl-ws_b200", "libb200sdr.so")
 
@@ -492,6 +493,21 @@ class DropIn(Ref):
         # the private copy lives in a temp dir, so its $ORIGIN rpath no longer finds the product
         # library: load it first, by path, into the global namespace
         C.CDLL(PRODUCT_SO, mode=C.RTLD_GLOBAL)
+
+
+class DropInAudio(DropIn):
+    """As DropIn, with audio_main.o replaced too: the unmodified main.c / cbb_main.c register and drain the
+    GPU demodulator of libb200audio.so (audio_main.h interface) -- atan2, limiter and both half-bands on the GPU."""
+
+    SO = DROPIN_AUDIO_SO
+
+    def _preload(self):
+        C.CDLL(PRODUCT_SO, mode=C.RTLD_GLOBAL)
+        C.CDLL(os.path.join(os.path.dirname(PRODUCT_SO), "libb200audio.so"), mode=C.RTLD_GLOBAL)
+
+
+def have_dropin_audio() -> bool:
+    return os.path.exists(DROPIN_AUDIO_SO) and os.path.exists(PRODUCT_SO)
 
 
 def have_dropin() -> bool:

@@ -9,7 +9,7 @@ module name ``rtl_ws_b200``.
 from . import audio, binding, replay, sharding, synth, wire  # noqa: F401
 from .binding import (  # noqa: F401
     B200Error, SpectrumPlan, StreamRing, Session, PushStream, RfDecimator, CicDelayLine,
-    fm_exec, chain_exec, init, lib, launch_count, fm_exec_cs32, FmDemod, audio_post, resample_taps, Comm,
+    fm_exec, chain_exec, init, lib, launch_count, fm_exec_cs32, FmDemod, debug_atan2, audio_post, resample_taps, Comm, Multi,
     shard_count, shard_stream, FM_STATE_FLOATS, FM_SKIP_STAGE2, AUDIO_DEEMPH_50US, AUDIO_DEEMPH_75US,
     AUDIO_RESAMPLE_48K, AUDIO_POST_STATE_FLOATS,
     spectrum_alloc, spectrum_free, spectrum_add_cmplx_u8, spectrum_add_cmplx_s32, spectrum_add_real_f32,

@@ -34,10 +34,10 @@ EXPORTED_SYMBOLS = [
     "b200_wire_audio_messages", "b200_wire_audio_fragment", "b200_wire_reference_drain_index",
     "b200_host_alloc", "b200_host_free",
     "b200_fm_exec_cs32", "b200_fm_demod_create", "b200_fm_demod_destroy", "b200_fm_demod_reset", "b200_fm_demod_block",
-    "b200_audio_post", "b200_audio_post_out_samples", "b200_audio_resample_taps",
+    "b200_debug_atan2", "b200_audio_post", "b200_audio_post_out_samples", "b200_audio_resample_taps",
     "b200_shard_count", "b200_shard_stream", "b200_comm_unique_id", "b200_comm_create", "b200_comm_create_all",
     "b200_comm_destroy", "b200_comm_world", "b200_comm_rank", "b200_comm_nccl_version", "b200_comm_gather_rows",
-    "b200_comm_gather_rows_all",
+    "b200_comm_gather_rows_all", "b200_multi_create", "b200_multi_destroy", "b200_multi_chain",
     "spectrum_alloc", "spectrum_add_cmplx_u8", "spectrum_add_cmplx_s32", "spectrum_add_real_f32", "spectrum_free",
     "cic_decimate", "halfband_decimate",
     "rf_decimator_alloc", "rf_decimator_add_callback", "rf_decimator_set_parameters",
@@ -131,6 +131,7 @@ def lib() -> C.CDLL:
     L.b200_fm_demod_destroy.argtypes = [vp]
     L.b200_fm_demod_reset.argtypes = [vp]
     L.b200_fm_demod_block.argtypes = [vp, vp, i32, vp, vp]
+    L.b200_debug_atan2.argtypes = [vp, i32, vp, i32, vp]
     L.b200_audio_post.argtypes = [vp, i64, i32, i64, C.c_double, i32, vp, vp, i64, vp]
     L.b200_audio_post_out_samples.restype = i64
     L.b200_audio_post_out_samples.argtypes = [i64, i32]
@@ -147,6 +148,11 @@ def lib() -> C.CDLL:
     L.b200_comm_rank.argtypes = [vp]
     L.b200_comm_gather_rows.argtypes = [vp, vp, i32, i32, vp, i32, vp]
     L.b200_comm_gather_rows_all.argtypes = [C.POINTER(vp), i32, C.POINTER(vp), i32, i32, vp, i32, C.POINTER(vp)]
+    L.b200_multi_create.restype = vp
+    L.b200_multi_create.argtypes = [i32, i32, i64, i32, i32]
+    L.b200_multi_destroy.restype = None
+    L.b200_multi_destroy.argtypes = [vp]
+    L.b200_multi_chain.argtypes = [vp, vp, i64, vp, vp, vp]
     # reference-named interface
     L.spectrum_alloc.restype = vp
     L.spectrum_alloc.argtypes = [i32]
@@ -374,6 +380,16 @@ def fm_exec_cs32(dec, state, audio=None, demod: bool = False, phase: bool = Fals
     return res
 
 
+def debug_atan2(y, x, which: int):
+    """atan2_approx of integer pairs as kernel family `which` evaluates it (b200_debug_atan2)."""
+    torch = _torch()
+    yx = torch.stack([torch.as_tensor(y, dtype=torch.int32), torch.as_tensor(x, dtype=torch.int32)], dim=-1).contiguous().cuda()
+    out = torch.empty(yx.shape[:-1], dtype=torch.float32, device="cuda")
+    _check(lib().b200_debug_atan2(C.c_void_p(yx.data_ptr()), out.numel(), C.c_void_p(out.data_ptr()), which,
+                                  _stream_ptr()), "b200_debug_atan2")
+    return out.cpu().numpy()
+
+
 class FmDemod:
     """b200_fm_demod_*: the body of an rf_decimator_callback -- host cmplx_s32 blocks in, host audio out."""
 
@@ -459,6 +475,31 @@ class Comm:
     def close(self):
         if getattr(self, "h", None):
             lib().b200_comm_destroy(self.h)
+            self.h = None
+
+
+class Multi:
+    """b200_multi_*: one process, G GPUs, host arrays in global stream order (stream s on device s mod G)."""
+
+    def __init__(self, n_gpus: int, n_streams: int, max_samples: int, gain_db: int = 0, K_avg: int = 6):
+        _torch()
+        self.n_gpus, self.n_streams = n_gpus, n_streams
+        self.h = lib().b200_multi_create(n_gpus, n_streams, max_samples, gain_db, K_avg)
+        if not self.h:
+            raise B200Error(f"b200_multi_create: {last_error()}")
+
+    def chain(self, h_iq: np.ndarray, n_samples: int, want_db: bool = True, want_audio: bool = True, want_avg: bool = True):
+        h_iq = np.ascontiguousarray(h_iq, dtype=np.uint8)
+        db = np.empty((self.n_streams, n_samples // 1024, 1024), np.float32) if want_db else None
+        audio = np.empty((self.n_streams, n_samples // 40), np.float32) if want_audio else None
+        avg = np.empty((self.n_streams, 1024), np.uint8) if want_avg else None
+        p = lambda a: a.ctypes.data if a is not None else None
+        _check(lib().b200_multi_chain(self.h, h_iq.ctypes.data, n_samples, p(db), p(audio), p(avg)), "b200_multi_chain")
+        return db, audio, avg
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200_multi_destroy(self.h)
             self.h = None
 
 

@@ -6,7 +6,7 @@
 // AudioContext (resources/rtl_ui.js:79-82) and plays the 51.2 kHz stream 6 % slow.  BASELINE.json's north
 // star names "de-emphasis and resampler ... 48 kHz audio", so both are offered as extensions that are
 // OFF by default: without flags nothing in this file runs and every output bit is the reference's.
-// The definitions (restated for the CPU in oracle/oracle.c: orc_deemphasis, orc_resample_15_16):
+// The definitions (the test oracle restates them as plain sequential loops):
 //
 //   de-emphasis   y[n] = y[n-1] + alpha * (x[n] - y[n-1]),  alpha = 1 - exp(-1 / (rate * tau)),
 //                 tau = 50 us (B200_AUDIO_DEEMPH_50US, Europe) or 75 us (.._75US, Americas), y[-1] = 0
@@ -149,7 +149,7 @@ bool g_taps_uploaded[64] = {false};
 
 }  // namespace
 
-// The 240-tap prototype, in double, rounded to float once (same statements as oracle/oracle.c: orc_resample_taps)
+// The 240-tap prototype, in double, rounded to float once (the test oracle evaluates the same statements)
 void audio_resample_taps(float* h)
 {
     const double pi = 3.14159265358979323846;

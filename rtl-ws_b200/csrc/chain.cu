@@ -42,6 +42,9 @@ b200_spectrum_plan* cached_plan(int K, int gain_db)
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     std::lock_guard<std::mutex> lock(g_plan_mutex);
+    // only the integer quotient gain_db / 10 reaches the arithmetic (cbb_main.c:112): one plan per decade,
+    // so a client sweeping `spectrumgain` does not grow the cache
+    gain_db = (gain_db / 10) * 10;
     auto key = std::make_tuple(dev, K, gain_db);
     auto it = g_plans.find(key);
     if (it != g_plans.end()) return it->second;
@@ -91,6 +94,16 @@ int b200_chain_exec_r(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_st
         return B200_ERR_ALIGN;
     }
     if (n_streams == 0 || n_samples == 0) return B200_OK;
+    if (d_audio != nullptr && n_samples < fm_history_samples(R)) {
+        // the carried state is the last 32 R input samples: a batch must hold at least that many
+        set_error("chain exec: a batch of %lld samples is shorter than the FM history (%d samples at R = %d)",
+                  (long long) n_samples, fm_history_samples(R), R);
+        return B200_ERR_ARG;
+    }
+    if (d_avg_u8 != nullptr && (K_avg < 1 || (int64_t) K_avg * CHAIN_N > n_samples)) {     // before anything is launched
+        set_error("chain exec: K_avg = %d does not fit the batch", K_avg);
+        return B200_ERR_ARG;
+    }
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     b200_spectrum_plan* pl = cached_plan(1, gain_db);
     if (pl == nullptr) return B200_ERR_CUDA;
@@ -114,10 +127,6 @@ int b200_chain_exec_r(const uint8_t* d_iq, int64_t stream_stride_bytes, int n_st
         }
     }
     if (d_avg_u8 != nullptr) {
-        if (K_avg < 1 || (int64_t) K_avg * CHAIN_N > n_samples) {
-            set_error("chain exec: K_avg = %d does not fit the batch", K_avg);
-            return B200_ERR_ARG;
-        }
         b200_spectrum_plan* avg = cached_plan(K_avg, gain_db);
         if (avg == nullptr) return B200_ERR_CUDA;
         rc = b200_spectrum_exec(avg, d_iq, stream_stride_bytes, n_streams, 1, nullptr, nullptr, d_avg_u8, cuda_stream);
@@ -145,6 +154,61 @@ struct b200_session {
     int device;
 };
 
+namespace b200 {
+
+// Submit one batch of every stream of the session without waiting: rows of the host arrays may be strided
+// (pitches in bytes for h_iq, in floats for h_db / h_audio), which is how a multi-GPU host hands each device
+// its streams s mod G of one global array.  d_avg_u8 (device, nullable): [n_streams][1024] payload rows.
+int session_chain_submit(b200_session* s, const uint8_t* h_iq, int64_t iq_pitch_bytes, int64_t n_samples, int gain_db,
+                         float* h_db, int64_t db_pitch, float* h_audio, int64_t audio_pitch, uint8_t* d_avg_u8, int K_avg)
+{
+    if (s == nullptr || h_iq == nullptr || n_samples < 0 || n_samples > s->max_samples || n_samples % s->tile != 0) {
+        set_error("session chain: n_samples %lld must be a multiple of %lld and at most %lld", (long long) n_samples,
+                  s ? (long long) s->tile : 0ll, s ? (long long) s->max_samples : 0ll);
+        return B200_ERR_ARG;
+    }
+    if (n_samples == 0) return B200_OK;
+    const int lanes = b200_session::LANES;
+    // stream groups small enough to pipeline H2D / kernels / D2H across the lanes
+    int group = (s->n_streams + 4 * lanes - 1) / (4 * lanes);
+    if (group < 1) group = 1;
+    const int64_t n_audio = n_samples / (4 * s->R);
+    int lane = 0;
+    for (int s0 = 0; s0 < s->n_streams; s0 += group, lane = (lane + 1) % lanes) {
+        const int ns = (s->n_streams - s0) < group ? (s->n_streams - s0) : group;
+        cudaStream_t st = s->streams[lane];
+        uint8_t* d_batch = s->d_ring + (int64_t) s0 * s->stride_bytes + 2 * (int64_t) s->hist_samples;
+        float* d_db = s->d_db + (size_t) s0 * (size_t) n_samples;
+        float* d_audio = s->d_audio + (size_t) s0 * (size_t) n_audio;
+        B200_CUDA_TRY(cudaMemcpy2DAsync(d_batch, (size_t) s->stride_bytes, h_iq + (size_t) s0 * (size_t) iq_pitch_bytes,
+                                        (size_t) iq_pitch_bytes, (size_t) (2 * n_samples), (size_t) ns,
+                                        cudaMemcpyHostToDevice, st));
+        const int rc = b200_chain_exec_r(d_batch, s->stride_bytes, ns, n_samples, s->R, gain_db, h_db ? d_db : nullptr,
+                                         h_audio ? d_audio : nullptr, n_audio, d_avg_u8 ? d_avg_u8 + (size_t) s0 * 1024 : nullptr,
+                                         K_avg, st);
+        if (rc) return rc;
+        if (h_db)
+            B200_CUDA_TRY(cudaMemcpy2DAsync(h_db + (size_t) s0 * (size_t) db_pitch, sizeof(float) * (size_t) db_pitch, d_db,
+                                            sizeof(float) * (size_t) n_samples, sizeof(float) * (size_t) n_samples,
+                                            (size_t) ns, cudaMemcpyDeviceToHost, st));
+        if (h_audio)
+            B200_CUDA_TRY(cudaMemcpy2DAsync(h_audio + (size_t) s0 * (size_t) audio_pitch, sizeof(float) * (size_t) audio_pitch,
+                                            d_audio, sizeof(float) * (size_t) n_audio, sizeof(float) * (size_t) n_audio,
+                                            (size_t) ns, cudaMemcpyDeviceToHost, st));
+        const int rc2 = launch_fm_history_carry(d_batch, s->stride_bytes, ns, n_samples, s->R, st);
+        if (rc2) return rc2;
+    }
+    return B200_OK;
+}
+
+int session_wait(b200_session* s)
+{
+    for (int i = 0; i < b200_session::LANES; ++i) B200_CUDA_TRY(cudaStreamSynchronize(s->streams[i]));
+    return B200_OK;
+}
+
+}  // namespace b200
+
 extern "C" {
 
 b200_session* b200_session_create(int n_streams, int64_t max_samples_per_batch)
@@ -159,8 +223,10 @@ b200_session* b200_session_create_r(int n_streams, int64_t max_samples_per_batch
         set_error("session: down factor %d outside [1, 256]", R);
         return nullptr;
     }
-    if (n_streams < 1 || max_samples_per_batch < tile || max_samples_per_batch % tile != 0) {
-        set_error("session: max_samples_per_batch must be a positive multiple of %lld", (long long) tile);
+    if (n_streams < 1 || max_samples_per_batch < tile || max_samples_per_batch % tile != 0 ||
+        max_samples_per_batch < fm_history_samples(R)) {
+        set_error("session: max_samples_per_batch must be a positive multiple of %lld and at least %d", (long long) tile,
+                  fm_history_samples(R));
         return nullptr;
     }
     b200_session* s = new b200_session();
@@ -209,41 +275,14 @@ void b200_session_reset(b200_session* s)
 int b200_session_chain(b200_session* s, const uint8_t* h_iq, int64_t n_samples, int gain_db, float* h_db,
                        float* h_audio)
 {
-    if (s == nullptr || h_iq == nullptr || n_samples < 0 || n_samples > s->max_samples || n_samples % s->tile != 0) {
-        set_error("session chain: n_samples %lld must be a multiple of %lld and at most %lld", (long long) n_samples,
-                  s ? (long long) s->tile : 0ll, s ? (long long) s->max_samples : 0ll);
+    if (s == nullptr) {
+        set_error("session chain: null session");
         return B200_ERR_ARG;
     }
-    if (n_samples == 0) return B200_OK;
-    const int lanes = b200_session::LANES;
-    // stream groups small enough to pipeline H2D / kernels / D2H across the lanes
-    int group = (s->n_streams + 4 * lanes - 1) / (4 * lanes);
-    if (group < 1) group = 1;
-    const int64_t n_audio = n_samples / (4 * s->R);
-    int lane = 0;
-    for (int s0 = 0; s0 < s->n_streams; s0 += group, lane = (lane + 1) % lanes) {
-        const int ns = (s->n_streams - s0) < group ? (s->n_streams - s0) : group;
-        cudaStream_t st = s->streams[lane];
-        uint8_t* d_batch = s->d_ring + (int64_t) s0 * s->stride_bytes + 2 * (int64_t) s->hist_samples;
-        float* d_db = s->d_db + (size_t) s0 * (size_t) n_samples;
-        float* d_audio = s->d_audio + (size_t) s0 * (size_t) n_audio;
-        B200_CUDA_TRY(cudaMemcpy2DAsync(d_batch, (size_t) s->stride_bytes, h_iq + (size_t) s0 * 2 * (size_t) n_samples,
-                                        (size_t) (2 * n_samples), (size_t) (2 * n_samples), (size_t) ns,
-                                        cudaMemcpyHostToDevice, st));
-        const int rc = b200_chain_exec_r(d_batch, s->stride_bytes, ns, n_samples, s->R, gain_db, h_db ? d_db : nullptr,
-                                         h_audio ? d_audio : nullptr, n_audio, nullptr, 0, st);
-        if (rc) return rc;
-        if (h_db)
-            B200_CUDA_TRY(cudaMemcpyAsync(h_db + (size_t) s0 * (size_t) n_samples, d_db,
-                                          sizeof(float) * (size_t) ns * (size_t) n_samples, cudaMemcpyDeviceToHost, st));
-        if (h_audio)
-            B200_CUDA_TRY(cudaMemcpyAsync(h_audio + (size_t) s0 * (size_t) n_audio, d_audio,
-                                          sizeof(float) * (size_t) ns * (size_t) n_audio, cudaMemcpyDeviceToHost, st));
-        const int rc2 = launch_fm_history_carry(d_batch, s->stride_bytes, ns, n_samples, s->R, st);
-        if (rc2) return rc2;
-    }
-    for (int i = 0; i < lanes; ++i) B200_CUDA_TRY(cudaStreamSynchronize(s->streams[i]));
-    return B200_OK;
+    const int rc = b200::session_chain_submit(s, h_iq, 2 * n_samples, n_samples, gain_db, h_db, n_samples, h_audio,
+                                              n_samples / (4 * s->R), nullptr, 0);
+    if (rc) return rc;
+    return b200::session_wait(s);
 }
 
 }  // extern "C"

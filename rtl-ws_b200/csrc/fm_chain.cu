@@ -378,8 +378,10 @@ int launch_fm_history_carry(uint8_t* iq, int64_t stride, int n_streams, int64_t 
         set_error("fm: batch shorter than the history (%d samples)", fm_history_samples(R));
         return B200_ERR_ARG;
     }
-    if ((reinterpret_cast<uintptr_t>(iq) & 15) != 0 || (stride & 15) != 0 || ((n_samples * 2) & 15) != 0)
+    if ((reinterpret_cast<uintptr_t>(iq) & 15) != 0 || (stride & 15) != 0 || ((n_samples * 2) & 15) != 0) {
+        set_error("fm history carry: pointer, stride and batch bytes must be multiples of 16");
         return B200_ERR_ALIGN;
+    }
     if (n_streams == 0) return B200_OK;
     const int64_t total = (int64_t) n_streams * (hist_bytes / 16);
     const int blocks = (int) ((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);

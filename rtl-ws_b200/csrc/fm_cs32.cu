@@ -164,6 +164,16 @@ __global__ void fm_cs32_commit_kernel(float* state, int n_streams)
     st[i % 21] = st[ST_NEXT + i % 21];
 }
 
+// diagnostic: the three device forms of atan2_approx on arbitrary integer pairs (tests pin each of them
+// to the reference's grid: tests/golden/atan2.npz)
+__global__ void atan2_forms_kernel(const int2* __restrict__ yx, int n, float* __restrict__ out, int which)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float y = (float) yx[i].x, x = (float) yx[i].y;
+    out[i] = which == 0 ? atan2_approx_dev(y, x) : (which == 1 ? atan2_approx_dev2(y, x) : atan2_approx_seq(y, x));
+}
+
 }  // namespace
 
 int launch_fm_cs32(const int32_t* d_dec, int64_t dec_stride, int n_streams, int64_t n_dec, float* d_state,
@@ -225,6 +235,19 @@ int b200_fm_exec_cs32(const int32_t* d_decimated, int64_t dec_stride, int n_stre
 }
 
 }  // extern "C"
+
+extern "C" int b200_debug_atan2(const int32_t* d_yx, int n, float* d_out, int which, void* cuda_stream)
+{
+    if (d_yx == nullptr || d_out == nullptr || n < 0 || which < 0 || which > 2) {
+        set_error("debug atan2: bad arguments");
+        return B200_ERR_ARG;
+    }
+    if (n == 0) return B200_OK;
+    atan2_forms_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+        reinterpret_cast<const int2*>(d_yx), n, d_out, which);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
 
 // ---- host-buffer demodulator: what an rf_decimator_callback calls -----------------------------------
 

@@ -345,3 +345,139 @@ int b200_comm_gather_rows_all(b200_comm** comms, int n, const void* const* d_sen
 }
 
 }  // extern "C"
+
+// ---- one process, G GPUs, host buffers: b200_multi ------------------------------------------------
+//
+// The host-buffer session of chain.cu, once per device, behind one object: stream s of the caller's global
+// arrays goes to device s mod G (rows of the host arrays are simply read and written with a pitch of G
+// rows, no repacking), every device runs the chain on its own streams concurrently, and the per-stream
+// payload rows are gathered on device 0 by b200_comm_gather_rows_all before they go back to the host.
+
+struct b200_session;
+namespace b200 {
+int session_chain_submit(b200_session* s, const uint8_t* h_iq, int64_t iq_pitch_bytes, int64_t n_samples, int gain_db,
+                         float* h_db, int64_t db_pitch, float* h_audio, int64_t audio_pitch, uint8_t* d_avg_u8, int K_avg);
+int session_wait(b200_session* s);
+}  // namespace b200
+
+struct b200_multi {
+    int G;
+    int n_streams;
+    int64_t max_samples;
+    int gain_db;
+    int K_avg;
+    std::vector<b200_session*> sess;       // per device, n_local streams (null if the device has none)
+    std::vector<b200_comm*> comms;
+    std::vector<uint8_t*> d_avg;           // per device: [n_local][1024]
+    uint8_t* d_all;                        // device 0: [n_streams][1024] in global stream order
+};
+
+extern "C" {
+
+void b200_multi_destroy(b200_multi* m)
+{
+    if (m == nullptr) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int g = 0; g < m->G; ++g) {
+        cudaSetDevice(g);
+        if (g < (int) m->sess.size() && m->sess[g]) b200_session_destroy(m->sess[g]);
+        if (g < (int) m->d_avg.size() && m->d_avg[g]) cudaFree(m->d_avg[g]);
+        if (g == 0 && m->d_all) cudaFree(m->d_all);
+    }
+    for (b200_comm* c : m->comms)
+        if (c) b200_comm_destroy(c);
+    cudaSetDevice(prev);
+    delete m;
+}
+
+b200_multi* b200_multi_create(int n_gpus, int n_streams, int64_t max_samples_per_batch, int gain_db, int K_avg)
+{
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || n_gpus < 1 || n_gpus > have) {
+        set_error("multi: %d GPUs asked for, %d visible", n_gpus, have);
+        return nullptr;
+    }
+    if (n_streams < 1 || K_avg < 0 || (int64_t) K_avg * 1024 > max_samples_per_batch) {
+        set_error("multi: bad arguments");
+        return nullptr;
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    b200_multi* m = new b200_multi();
+    m->G = n_gpus;
+    m->n_streams = n_streams;
+    m->max_samples = max_samples_per_batch;
+    m->gain_db = gain_db;
+    m->K_avg = K_avg;
+    m->d_all = nullptr;
+    m->sess.assign((size_t) n_gpus, nullptr);
+    m->d_avg.assign((size_t) n_gpus, nullptr);
+    m->comms.assign((size_t) n_gpus, nullptr);
+    bool ok = true;
+    for (int g = 0; g < n_gpus && ok; ++g) {
+        const int n_local = shard_count(n_streams, n_gpus, g);
+        ok = cudaSetDevice(g) == cudaSuccess;
+        if (ok && n_local > 0) {
+            m->sess[g] = b200_session_create(n_local, max_samples_per_batch);
+            ok = m->sess[g] != nullptr && cudaMalloc((void**) &m->d_avg[g], (size_t) n_local * 1024) == cudaSuccess;
+        }
+        if (ok && g == 0) ok = cudaMalloc((void**) &m->d_all, (size_t) n_streams * 1024) == cudaSuccess;
+    }
+    if (ok && K_avg > 0 && n_gpus > 1) ok = b200_comm_create_all(n_gpus, m->comms.data()) == B200_OK;
+    cudaSetDevice(prev);
+    if (!ok) {
+        if (b200_last_error()[0] == 0) set_error("multi: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        b200_multi_destroy(m);
+        return nullptr;
+    }
+    return m;
+}
+
+int b200_multi_chain(b200_multi* m, const uint8_t* h_iq, int64_t n_samples, float* h_db, float* h_audio, uint8_t* h_avg_u8)
+{
+    if (m == nullptr || h_iq == nullptr || (h_avg_u8 != nullptr && m->K_avg < 1)) {
+        set_error("multi chain: bad arguments (payload rows need K_avg >= 1 at create)");
+        return B200_ERR_ARG;
+    }
+    int prev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&prev));
+    const int G = m->G;
+    const int64_t n_audio = n_samples / 40;
+    int rc = B200_OK;
+    for (int g = 0; g < G && rc == B200_OK; ++g) {          // every device gets its streams s mod G; nothing waits yet
+        if (m->sess[g] == nullptr) continue;
+        cudaSetDevice(g);
+        rc = session_chain_submit(m->sess[g], h_iq + (size_t) g * 2 * (size_t) n_samples, (int64_t) G * 2 * n_samples, n_samples,
+                                  m->gain_db, h_db ? h_db + (size_t) g * (size_t) n_samples : nullptr, (int64_t) G * n_samples,
+                                  h_audio ? h_audio + (size_t) g * (size_t) n_audio : nullptr, (int64_t) G * n_audio,
+                                  h_avg_u8 ? m->d_avg[g] : nullptr, m->K_avg);
+    }
+    for (int g = 0; g < G; ++g) {
+        if (m->sess[g] == nullptr) continue;
+        cudaSetDevice(g);
+        const int rw = session_wait(m->sess[g]);
+        if (rc == B200_OK) rc = rw;
+    }
+    if (rc == B200_OK && h_avg_u8 != nullptr) {
+        cudaSetDevice(0);
+        if (G > 1) {
+            std::vector<const void*> sends((size_t) G);
+            for (int g = 0; g < G; ++g) sends[g] = m->d_avg[g];
+            rc = b200_comm_gather_rows_all(m->comms.data(), G, sends.data(), m->n_streams, 1024, m->d_all, 0, nullptr);
+        } else if (cudaMemcpy(m->d_all, m->d_avg[0], (size_t) m->n_streams * 1024, cudaMemcpyDeviceToDevice) != cudaSuccess) {
+            rc = B200_ERR_CUDA;
+        }
+        if (rc == B200_OK) {
+            cudaSetDevice(0);
+            if (cudaMemcpy(h_avg_u8, m->d_all, (size_t) m->n_streams * 1024, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                set_error("multi chain: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = B200_ERR_CUDA;
+            }
+        }
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+}  // extern "C"

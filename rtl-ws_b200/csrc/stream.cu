@@ -190,8 +190,10 @@ b200_stream* b200_stream_create_r(int n_streams, int64_t batch_samples, int gain
         set_error("stream: down factor %d outside [1, 256]", R);
         return nullptr;
     }
-    if (n_streams < 1 || batch_samples < tile || batch_samples % tile != 0) {
-        set_error("stream: batch_samples must be a positive multiple of %lld", (long long) tile);
+    if (n_streams < 1 || batch_samples < tile || batch_samples % tile != 0 || batch_samples < fm_history_samples(R)) {
+        // (the FM state is the last 32 R input samples: at R > 32 one tile is shorter than that)
+        set_error("stream: batch_samples must be a positive multiple of %lld and at least %d", (long long) tile,
+                  fm_history_samples(R));
         return nullptr;
     }
     b200_stream* s = new b200_stream();

@@ -32,6 +32,20 @@ def test_library_exports_every_declared_symbol(pkg):
     assert set(pkg.EXPORTED_SYMBOLS) == want
 
 
+def test_audio_library_exports_the_reference_audio_interface(pkg):
+    """libb200audio.so = audio_main.h:6-14 (+ extensions), declared in include/rtlws_audio_compat.h."""
+    lib = pkg.audio.lib()
+    want = declared_functions("rtlws_audio_compat.h")
+    assert {"audio_init", "audio_new_audio_available", "audio_get_audio_payload", "audio_fm_demodulator",
+            "audio_close"} <= want
+    missing = sorted(n for n in want if not hasattr(lib, n))
+    assert not missing, f"declared in include/rtlws_audio_compat.h but not exported: {missing}"
+    assert set(pkg.audio.EXPORTED_SYMBOLS) == want
+    # host plumbing only: the arithmetic lives behind the C ABI of libb200sdr.so
+    blob = open(pkg.audio.LIB_PATH, "rb").read()
+    assert b"libb200sdr.so" in blob and b"libcudart" not in blob
+
+
 def test_compat_types_have_reference_layout(pkg):
     # common_sp.h:7-20: 2-byte cmplx_u8, 8-byte cmplx_s32; resample.h:8-12: two cmplx_s32
     assert ctypes.sizeof(pkg.binding.CmplxS32) == 8
@@ -77,6 +91,7 @@ def test_headers_are_plain_c_and_the_c_hosts_link(pkg, tmp_path):
         subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + inc, "-c", str(src),
                         "-o", str(tmp_path / (header + ".o"))], check=True)
     for rel, libs in (("examples/virtual_dongles.c", ["-lb200sdr", "-lb200replay", "-lm"]),
+                      ("examples/multi_gpu_gather.c", ["-lb200sdr"]),
                       ("tools/push_bench.c", ["-lb200sdr"])):
         subprocess.run(["gcc", "-O1", "-pthread", "-Wall", "-o", str(tmp_path / os.path.basename(rel)[:-2]),
                         os.path.join(ROOT, rel), "-I" + inc, "-L" + lib_dir, "-Wl,-rpath," + lib_dir] + libs, check=True)

@@ -258,3 +258,34 @@ def test_chain_rejects_bad_parameters(po):
         po.Chain(0.0, 10)
     with pytest.raises(ValueError):
         po.Chain(2048000.0, 0)
+
+
+# ---- definitions of the product's opt-in extensions (no reference counterpart) ------------------------
+
+def test_extension_definitions_deemphasis_and_resampler(po):
+    """The reference has neither (audio_main.c:133-139 ends at 51.2 kS/s, no de-emphasis); these are the
+    definitions csrc/audio_post.cu is checked against, so pin their basic properties."""
+    h = po.resample_taps()
+    assert h.shape == (240,) and np.allclose(h, h[::-1], atol=1e-9)            # linear phase
+    assert abs(h.sum() - 15.0) < 1e-4
+    assert all(abs(h[r::15].sum() - 1.0) < 5e-5 for r in range(15))            # unity DC gain in every phase
+    x = np.ones(16 * 40, np.float32)
+    y, hist = po.resample_15_16(x)
+    assert len(y) == 15 * 40 and np.abs(y[30:] - 1.0).max() < 5e-5 and np.array_equal(hist, np.ones(15, np.float32))
+    # split input = same output (the history carries)
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, 16 * 64).astype(np.float32)
+    whole, _ = po.resample_15_16(x)
+    a, hist = po.resample_15_16(x[:16 * 10])
+    b, _ = po.resample_15_16(x[16 * 10:], hist)
+    assert np.array_equal(np.concatenate([a, b]), whole)
+    with pytest.raises(ValueError):
+        po.resample_15_16(x[:24])
+    # de-emphasis: first-order low-pass with the textbook time constant, -3 dB at 1 / (2 pi tau)
+    y, st = po.deemphasis(np.ones(4096, np.float32), 51200.0, 75e-6)
+    alpha = 1 - np.exp(-1 / (51200.0 * 75e-6))
+    assert abs(y[0] - alpha) < 1e-6 and abs(y[-1] - 1.0) < 1e-5 and st[0] == y[-1]
+    t = np.arange(51200) / 51200.0
+    f3 = 1 / (2 * np.pi * 75e-6)
+    y, _ = po.deemphasis(np.sin(2 * np.pi * f3 * t).astype(np.float32), 51200.0, 75e-6)
+    assert abs(20 * np.log10(np.abs(y[5000:]).max()) + 3.0) < 0.35             # bilinear-free one-pole: close to -3 dB
