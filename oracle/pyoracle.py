@@ -491,8 +491,10 @@ class DropIn(Ref):
 
     def _preload(self):
         # the private copy lives in a temp dir, so its $ORIGIN rpath no longer finds the product
-        # library: load it first, by path, into the global namespace
-        C.CDLL(PRODUCT_SO, mode=C.RTLD_GLOBAL)
+        # library: load it first, by path; the copy's DT_NEEDED entry then matches it by soname.
+        # NOT into the global namespace: the product exports the reference's own symbol names, and a
+        # global copy would interpose them into every Ref() loaded afterwards
+        C.CDLL(PRODUCT_SO)
 
 
 class DropInAudio(DropIn):
@@ -502,8 +504,8 @@ class DropInAudio(DropIn):
     SO = DROPIN_AUDIO_SO
 
     def _preload(self):
-        C.CDLL(PRODUCT_SO, mode=C.RTLD_GLOBAL)
-        C.CDLL(os.path.join(os.path.dirname(PRODUCT_SO), "libb200audio.so"), mode=C.RTLD_GLOBAL)
+        C.CDLL(PRODUCT_SO)
+        C.CDLL(os.path.join(os.path.dirname(PRODUCT_SO), "libb200audio.so"))
 
 
 def have_dropin_audio() -> bool:

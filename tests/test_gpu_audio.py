@@ -43,7 +43,9 @@ def test_atan2_forms_on_the_reference_grid(pkg, cuda, which):
 def test_fm_exec_cs32_matches_oracle_with_state_carry(pkg, cuda, po, synth):
     torch = cuda
     n_streams = 3
-    blocks = [20480, 4, 1024 + 8, 20480, 12, 4096]            # incl. blocks shorter than the ten-float delay lines
+    # every block leaves >= 10 first-stage outputs: below that resample.c:66 reads in front of its input buffer
+    # (undefined in the reference and in its port); shorter blocks are covered by the chunking test below
+    blocks = [20480, 40, 1024 + 8, 20480, 44, 4096]
     decs = [_decimated(po, synth, 10 * sum(blocks), seed=300 + s) for s in range(n_streams)]
     state = torch.zeros((n_streams, pkg.FM_STATE_FLOATS), dtype=torch.float32, device="cuda")
     sts = [po.FmState() for _ in range(n_streams)]
@@ -65,6 +67,25 @@ def test_fm_exec_cs32_matches_oracle_with_state_carry(pkg, cuda, po, synth):
         assert abs(st[s, 0] - sts[s].prev_sample) <= 1e-6
         assert np.abs(st[s, 1:11] - np.array(sts[s].delay_line_1[:])).max() <= 2e-6
         assert np.abs(st[s, 11:21] - np.array(sts[s].delay_line_2[:])).max() <= 1e-5
+
+
+def test_fm_exec_cs32_does_not_depend_on_chunking(pkg, cuda, po, synth):
+    """Blocks of any multiple of 4 -- also shorter than the delay lines, where the reference itself reads out of
+    bounds (resample.c:66) -- continue the stream exactly: same audio as one long block, bit for bit."""
+    torch = cuda
+    dec = _decimated(po, synth, 10 * 4096, seed=41)
+    d_all = torch.as_tensor(dec[None]).cuda()
+    state = torch.zeros((1, pkg.FM_STATE_FLOATS), dtype=torch.float32, device="cuda")
+    whole = pkg.fm_exec_cs32(d_all, state)["audio"][0].cpu().numpy()
+    state.zero_()
+    parts, pos = [], 0
+    for n in [4, 8, 4, 12, 1024, 4, 2048 - 32, 20, 4, 4, 4096 - 2048 - 1024 - 28]:
+        parts.append(pkg.fm_exec_cs32(d_all[:, pos:pos + n].contiguous(), state)["audio"][0].cpu().numpy())
+        pos += n
+    assert pos == 4096
+    assert np.array_equal(np.concatenate(parts), whole)
+    _, _, want, _ = po.fm_demodulate(dec)
+    assert np.abs(whole - want).max() <= 1e-5
 
 
 def test_fm_exec_cs32_large_inputs_and_argument_errors(pkg, cuda, po):
