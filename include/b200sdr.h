@@ -208,6 +208,12 @@ void b200_session_destroy(b200_session* s);
 void b200_session_reset(b200_session* s);      /* all streams back to stream start */
 int b200_session_chain(b200_session* s, const uint8_t* h_iq, int64_t n_samples, int gain_db,
                        float* h_db, float* h_audio);
+/* The same call returning what the reference itself hands its clients instead of per-frame rows: the audio
+ * (nullable) and, per stream, the 1024 payload bytes of the K_avg-frame average at the start of the batch
+ * (cbb_main.c:40-70 + 106-135; K_avg = 6 is the reference's FFT_AVERAGE).  0.1 B per input sample come back
+ * over PCIe instead of 4.1.  h_avg_u8: [n_streams][1024]. */
+int b200_session_products(b200_session* s, const uint8_t* h_iq, int64_t n_samples, int gain_db, int K_avg,
+                          float* h_audio, uint8_t* h_avg_u8);
 /* ---- push-style streaming: what a signal_source callback calls ------------------------------
  *
  * signal_source.c:29-35 hands every registered callback a BORROWED buffer of cmplx_u8 and its

@@ -8,7 +8,7 @@
  * whole streams (streams are independent).
  *
  *   ref_bench <iq_file> <n_streams> <samples_per_stream> <n_workers> <mode> [unique]
- *       mode: chain | spectrum | fm
+ *       mode: chain | spectrum | fm | products
  *       unique: the file holds this many distinct captures (default n_streams); stream s reads
  *               capture s mod unique, so a long run does not need a multi-gigabyte file
  *
@@ -17,7 +17,10 @@
  *   - spectrum: EVERY 1024-sample frame goes through spectrum_add_cmplx_u8 into a zeroed
  *     double[1024] (cbb_main.c:50-54 with one frame per estimate) and the 10*log10
  *     epilogue of cbb_main.c:125 is applied per bin and stored as float (no truncation);
- *   - fm: rf_decimator_decimate_cmplx_u8 -> cic_decimate -> audio_fm_demodulator.
+ *   - fm: rf_decimator_decimate_cmplx_u8 -> cic_decimate -> audio_fm_demodulator;
+ *   - products: what the reference actually hands its clients -- fm as above plus, once per
+ *     PRODUCT_PERIOD samples (250 ms at 2.048 MS/s: cbb_main.c:16 SPECTRUM_EST_MS), the
+ *     FFT_AVERAGE = 6 frame average and its payload bytes (cbb_main.c:40-70, 106-135).
  * The FFT inside spectrum.c is the stand-in of oracle/fftw3_shim (FFTW3 is not installed).
  *
  * Prints one JSON object on stdout.
@@ -44,6 +47,8 @@ extern int64_t ref_fm_n_audio(void);
 
 #define FFT_POINTS 1024
 #define SOURCE_BUF_SAMPLES 131072
+#define PRODUCT_PERIOD 512000          /* 250 ms of IQ at rtl_sensor.c:12's 2.048 MS/s */
+#define FFT_AVERAGE 6                  /* cbb_main.c:18 */
 
 static double now_s(void)
 {
@@ -64,6 +69,7 @@ static void run_stream(const uint8_t* iq, int64_t n, int do_spec, int do_fm,
                        double* checksum)
 {
     int64_t pos = 0;
+    int64_t next_product = 0;
     double ps[FFT_POINTS];
     if (do_fm)
         ref_fm_set_outputs(NULL, 0, audio_out, audio_cap);
@@ -72,7 +78,26 @@ static void run_stream(const uint8_t* iq, int64_t n, int do_spec, int do_fm,
         int len = (int) ((n - pos) < SOURCE_BUF_SAMPLES ? (n - pos) : SOURCE_BUF_SAMPLES);
         if (do_fm)
             ref_fm_push(iq + 2 * pos, len, len);
-        if (do_spec)
+        if (do_spec == 2)
+        {
+            /* cbb_main.c:48-59 at the first frames of every period, then cbb_main.c:121-130 */
+            for (; next_product + FFT_AVERAGE * FFT_POINTS <= pos + len; next_product += PRODUCT_PERIOD)
+            {
+                const int64_t p0 = next_product;
+                int f, i;
+                unsigned char* payload = (unsigned char*) db_out;
+                memset(ps, 0, sizeof(ps));
+                for (f = 0; f < FFT_AVERAGE; f++)
+                    spectrum_add_cmplx_u8(spect, (const cmplx_u8*) (iq + 2 * (p0 + (int64_t) f * FFT_POINTS)), ps, FFT_POINTS);
+                for (i = 0; i < FFT_POINTS; i++)
+                {
+                    int m = (int) (10 * log10(fabs(ps[i] / FFT_AVERAGE)));
+                    payload[i] = (unsigned char) (m < 0 ? 0 : (m > 255 ? 255 : m));
+                }
+                *checksum += payload[17];
+            }
+        }
+        else if (do_spec)
         {
             int frames = len / FFT_POINTS;
             int f, i;
@@ -106,7 +131,7 @@ int main(int argc, char** argv)
 
     if (argc < 6)
     {
-        fprintf(stderr, "usage: %s <iq_file> <n_streams> <samples_per_stream> <n_workers> <chain|spectrum|fm> [unique]\n", argv[0]);
+        fprintf(stderr, "usage: %s <iq_file> <n_streams> <samples_per_stream> <n_workers> <chain|spectrum|fm|products> [unique]\n", argv[0]);
         return 2;
     }
     path = argv[1];
@@ -114,6 +139,7 @@ int main(int argc, char** argv)
     per_stream = atoll(argv[3]);
     n_workers = atoi(argv[4]);
     do_spec = strcmp(argv[5], "fm") != 0;
+    if (strcmp(argv[5], "products") == 0) do_spec = 2;
     do_fm = strcmp(argv[5], "spectrum") != 0;
     unique = argc > 6 ? atoi(argv[6]) : n_streams;
     if (unique < 1 || unique > n_streams) unique = n_streams;

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "b200_spectrum_exec_cs32", "b200_spectrum_exec_rf32",
     "b200_fm_history_samples", "b200_fm_history_reset", "b200_fm_history_carry", "b200_fm_exec",
     "b200_chain_exec", "b200_chain_exec_r", "b200_chain_tile_samples",
-    "b200_session_create", "b200_session_create_r", "b200_session_destroy", "b200_session_reset", "b200_session_chain",
+    "b200_session_create", "b200_session_create_r", "b200_session_destroy", "b200_session_reset", "b200_session_chain", "b200_session_products",
     "b200_stream_create", "b200_stream_create_r", "b200_stream_destroy", "b200_stream_set_sinks", "b200_stream_set_payload_sink", "b200_stream_push", "b200_stream_poll",
     "b200_stream_flush", "b200_stream_pending_samples",
     "b200_wire_spectrum_header", "b200_wire_spectrum_message", "b200_wire_spectrum_messages",
@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
     L.b200_session_destroy.argtypes = [vp]
     L.b200_session_reset.argtypes = [vp]
     L.b200_session_chain.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.b200_session_products.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     L.b200_stream_create.restype = vp
     L.b200_stream_create.argtypes = [i32, i64, i32]
     L.b200_stream_destroy.argtypes = [vp]
@@ -543,6 +544,16 @@ class Session:
             return C.c_void_p(x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data)
         _check(lib().b200_session_chain(self.h, hp(h_iq), n_samples, gain_db, hp(h_db), hp(h_audio)),
                "b200_session_chain")
+
+
+    def products(self, h_iq, n_samples: int, h_audio, h_avg_u8, gain_db: int = 0, K_avg: int = 6) -> None:
+        """b200_session_products: audio + the K-frame averaged payload bytes per stream (the reference's own products)."""
+        def hp(x):
+            if x is None:
+                return None
+            return C.c_void_p(x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data)
+        _check(lib().b200_session_products(self.h, hp(h_iq), n_samples, gain_db, K_avg, hp(h_audio), hp(h_avg_u8)),
+               "b200_session_products")
 
 
 class PushStream:

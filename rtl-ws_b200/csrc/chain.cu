@@ -149,6 +149,7 @@ struct b200_session {
     uint8_t* d_ring;           // [n_streams][stride_bytes]
     float* d_db;               // [n_streams][max_samples]            (1024 bins per 1024 samples)
     float* d_audio;            // [n_streams][max_samples / (4R)]
+    uint8_t* d_avg;            // [n_streams][1024] payload rows, allocated on first use (b200_session_products)
     static constexpr int LANES = 4;
     cudaStream_t streams[LANES];
     int device;
@@ -261,6 +262,7 @@ void b200_session_destroy(b200_session* s)
     if (s->d_ring) cudaFree(s->d_ring);
     if (s->d_db) cudaFree(s->d_db);
     if (s->d_audio) cudaFree(s->d_audio);
+    if (s->d_avg) cudaFree(s->d_avg);
     delete s;
 }
 
@@ -283,6 +285,23 @@ int b200_session_chain(b200_session* s, const uint8_t* h_iq, int64_t n_samples, 
                                               n_samples / (4 * s->R), nullptr, 0);
     if (rc) return rc;
     return b200::session_wait(s);
+}
+
+int b200_session_products(b200_session* s, const uint8_t* h_iq, int64_t n_samples, int gain_db, int K_avg,
+                          float* h_audio, uint8_t* h_avg_u8)
+{
+    if (s == nullptr || h_avg_u8 == nullptr || K_avg < 1) {
+        set_error("session products: bad arguments");
+        return B200_ERR_ARG;
+    }
+    if (s->d_avg == nullptr) B200_CUDA_TRY(cudaMalloc((void**) &s->d_avg, (size_t) s->n_streams * 1024));
+    int rc = b200::session_chain_submit(s, h_iq, 2 * n_samples, n_samples, gain_db, nullptr, 0, h_audio,
+                                        n_samples / (4 * s->R), s->d_avg, K_avg);
+    if (rc) return rc;
+    rc = b200::session_wait(s);
+    if (rc) return rc;
+    B200_CUDA_TRY(cudaMemcpy(h_avg_u8, s->d_avg, (size_t) s->n_streams * 1024, cudaMemcpyDeviceToHost));
+    return B200_OK;
 }
 
 }  // extern "C"
