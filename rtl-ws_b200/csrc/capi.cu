@@ -2,6 +2,7 @@
 // Host code only; every arithmetic step happens in the kernels of this directory.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -77,11 +78,14 @@ int cached_occupancy(const void* kernel, int block_threads, int smem_bytes)
 
 // launchers implemented next to their kernels
 int launch_spectrum1024(const SpecParams& p, cudaStream_t stream);
-int launch_spectrum_generic(const SpecParams& p, int N, int kind, cudaStream_t stream);
+int launch_spectrum_generic(const SpecParams& p, int N, int kind, float2* scratch, float* acc_scratch, int scratch_ctas,
+                            cudaStream_t stream);
+int spectrum_generic_scratch_ctas();
 int launch_spectrum4096(const SpecParams& p, cudaStream_t stream);
 int launch_spectrum2048(const SpecParams& p, cudaStream_t stream);
 int launch_spectrum_mx1024(const SpecParams& p, int N, cudaStream_t stream);
 int launch_spectrum64k(const SpecParams& p, const Spec64kExtra& x, cudaStream_t stream);
+int launch_spectrum64k_cluster(const SpecParams& p, const Spec64kExtra& x, cudaStream_t stream);
 int launch_fm_chain(const FmParams& p, cudaStream_t stream);
 int launch_fm_history_carry(uint8_t* iq, int64_t stride, int n_streams, int64_t n_samples, int R, cudaStream_t stream);
 int launch_fm_history_reset(uint8_t* iq, int64_t stride, int n_streams, int R, cudaStream_t stream);
@@ -107,7 +111,30 @@ struct b200_spectrum_plan {
     float* d_window;
     Spec64kExtra x64;              // N = 65536 only (all null otherwise)
     int device;
+    // Scratch that belongs to the plan (x64.scratch / x64.acc, and the generic kernel's global work arrays for
+    // N > 8192) is shared by every exec of the plan: execs on different CUDA streams are ordered through
+    // `scratch_done`, recorded after each launch that touched the scratch and awaited before the next one.
+    std::mutex scratch_mutex;
+    cudaEvent_t scratch_done;
+    bool scratch_used;
+    float2* gen_scratch;           // [gen_ctas][2][N] complex, generic kernel, N > 8192
+    float* gen_acc;                // [gen_ctas][N]
+    int gen_ctas;
 };
+
+// Run `launch` (which enqueues a kernel using the plan's scratch on `stream`) after every earlier user of the scratch.
+template <class F>
+static int with_plan_scratch(b200_spectrum_plan* plan, cudaStream_t stream, F launch)
+{
+    std::lock_guard<std::mutex> lock(plan->scratch_mutex);
+    if (plan->scratch_done == nullptr) B200_CUDA_TRY(cudaEventCreateWithFlags(&plan->scratch_done, cudaEventDisableTiming));
+    if (plan->scratch_used) B200_CUDA_TRY(cudaStreamWaitEvent(stream, plan->scratch_done, 0));
+    const int rc = launch();
+    if (rc != B200_OK) return rc;
+    B200_CUDA_TRY(cudaEventRecord(plan->scratch_done, stream));
+    plan->scratch_used = true;
+    return B200_OK;
+}
 
 static float2* upload_twiddles(int N)
 {
@@ -199,6 +226,11 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
     pl->d_twiddle_rk = nullptr;
     pl->d_twiddle_4k = nullptr;
     memset(&pl->x64, 0, sizeof(pl->x64));
+    pl->scratch_done = nullptr;
+    pl->scratch_used = false;
+    pl->gen_scratch = nullptr;
+    pl->gen_acc = nullptr;
+    pl->gen_ctas = 0;
     pl->d_twiddle = upload_twiddles(N);
     const bool wants1024 = (N == 2048 || N == 4096 || N == 8192 || N == 65536);
     if (pl->d_twiddle != nullptr && wants1024) pl->d_twiddle1024 = upload_twiddles(1024);
@@ -285,6 +317,9 @@ void b200_spectrum_plan_destroy(b200_spectrum_plan* plan)
     if (plan->x64.twiddle_rk) cudaFree((void*) plan->x64.twiddle_rk);
     if (plan->x64.scratch) cudaFree(plan->x64.scratch);
     if (plan->x64.acc) cudaFree(plan->x64.acc);
+    if (plan->gen_scratch) cudaFree(plan->gen_scratch);
+    if (plan->gen_acc) cudaFree(plan->gen_acc);
+    if (plan->scratch_done) cudaEventDestroy(plan->scratch_done);
     delete plan;
 }
 
@@ -342,7 +377,14 @@ static int spectrum_exec_kind(b200_spectrum_plan* plan, const void* d_in, int64_
         }
         p.twiddle = plan->d_twiddle1024;
         p.twiddle_n = plan->N == 65536 ? plan->d_twiddle : plan->d_twiddle_rk;
-        if (plan->N == 65536) return launch_spectrum64k(p, plan->x64, stream);
+        if (plan->N == 65536) {
+            // K = 1 rows run on four-CTA clusters with Z in distributed shared memory (spectrum64k_cluster.cu);
+            // K > 1 rows keep the scratch kernel.  B200_S64K_SCRATCH=1 forces the scratch kernel (A/B measurements).
+            const char* env = getenv("B200_S64K_SCRATCH");
+            const bool force_scratch = env != nullptr && atoi(env) != 0;
+            if (plan->K == 1 && !force_scratch) return launch_spectrum64k_cluster(p, plan->x64, stream);
+            return with_plan_scratch(plan, stream, [&] { return launch_spectrum64k(p, plan->x64, stream); });
+        }
         if (plan->N == 4096) {
             p.twiddle_n = plan->d_twiddle_4k;
             return launch_spectrum4096(p, stream);
@@ -353,7 +395,32 @@ static int spectrum_exec_kind(b200_spectrum_plan* plan, const void* d_in, int64_
         }
         return launch_spectrum_mx1024(p, plan->N, stream);
     }
-    return launch_spectrum_generic(p, plan->N, kind, stream);
+    if (plan->N <= 8192) return launch_spectrum_generic(p, plan->N, kind, nullptr, nullptr, 0, stream);
+    // N > 8192 on the generic kernel (16384 / 32768 from bytes, any N > 8192 from s32 / f32 input): its per-CTA work
+    // arrays live in the plan, on the plan's device, allocated on first use
+    {
+        std::lock_guard<std::mutex> lock(plan->scratch_mutex);
+        if (plan->gen_scratch == nullptr) {
+            int dev = -1;
+            B200_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev != plan->device) {
+                set_error("spectrum exec: the plan was created on device %d, the current device is %d", plan->device, dev);
+                return B200_ERR_ARG;
+            }
+            const int ctas = spectrum_generic_scratch_ctas();
+            B200_CUDA_TRY(cudaMalloc(&plan->gen_scratch, (size_t) ctas * 2 * plan->N * sizeof(float2)));
+            if (cudaMalloc(&plan->gen_acc, (size_t) ctas * plan->N * sizeof(float)) != cudaSuccess) {
+                set_error("spectrum exec: scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+                cudaFree(plan->gen_scratch);
+                plan->gen_scratch = nullptr;
+                return B200_ERR_CUDA;
+            }
+            plan->gen_ctas = ctas;
+        }
+    }
+    return with_plan_scratch(plan, stream, [&] {
+        return launch_spectrum_generic(p, plan->N, kind, plan->gen_scratch, plan->gen_acc, plan->gen_ctas, stream);
+    });
 }
 
 int b200_spectrum_exec(b200_spectrum_plan* plan, const uint8_t* d_iq, int64_t stream_stride_bytes, int n_streams,

@@ -223,6 +223,15 @@ struct ChainJobsCfg {
     static constexpr int SMEM = G * GROUP_SMEM + TW_BYTES;
     static_assert(SMEM <= 232448, "more shared memory than a CTA may have on sm_100");
     static_assert(CF_STAGE_BYTES % 128 == 0, "ring stages must stay 128-byte aligned");
+    // A waiter tests the PARITY of a barrier phase, so it must never get two phases ahead of the barrier: no job of
+    // tile it + S (or it + D) may be claimed while a job of tile it is still running.  Jobs are claimed in order and
+    // at most W are in flight, so the first job of tile it + S (number 6 (it + S)) is claimed after job
+    // 6 (it + S) - W + 1 - 1 has been claimed and ... finished only if it is older than every running job:
+    // 6 (it + S) - (W - 1) > 6 it + 5.  (W = 20, S = 3 broke exactly this at kernel start: measured, 78 dB off.)
+    static_assert(W <= 6 * S - 5, "ring too shallow for this many warps: a full[] waiter could lap the barrier");
+    // demod[] buffers: the audio job of tile it (job 6 (it + 1)) waits for phase it / D of demod_full[it % D]; it would
+    // pass a phase early if the audio job of tile it - D (6 D jobs older) had not passed its own wait yet
+    static_assert(W <= 6 * D, "too few demod buffers for this many warps");
 };
 
 template <int W, int G, int S, int D, bool TWS>
@@ -429,7 +438,6 @@ int launch_chain_fused(const uint8_t* d_iq, int64_t stride, int n_streams, int64
         case 4: return launch_chain_jobs<6, 2, 4, 4, true>(p, total, stream);
         case 5: return launch_chain_jobs<14, 1, 5, 5, true>(p, total, stream);
         case 6: return launch_chain_jobs<18, 1, 4, 4, true>(p, total, stream);
-        case 7: return launch_chain_jobs<20, 1, 3, 4, true>(p, total, stream);
         default: break;
     }
     if (int rc = ensure_dynamic_smem((const void*) chain_fused_kernel, CF_SMEM)) return rc;

@@ -1,0 +1,394 @@
+// spectrum64k_cluster.cu -- 65536-point power spectra (BASELINE config 4: wideband spectrogram, Hann
+// window, 50 % overlap) on a CLUSTER of four CTAs whose shared memories hold the whole intermediate
+// array: nothing but the IQ bytes and the finished rows ever touches L2 / HBM (sm_100a).
+//
+// Same four-step factorisation as spectrum64k.cu (which stays for K > 1 rows):
+//   65536 = 64 x 1024,  X[k + 1024 q] = sum_{r<64} W_64^(r q) * ( W_N^(r k) * F_r[k] ),  F_r = FFT_1024( x[64 m + r] )
+// but the 512 KB of Z[r][k] = W_N^(r k) F_r[k] no longer go through a global scratch.  The four CTAs of a
+// cluster take one frame together:
+//   phase 1  CTA c owns the polyphase branches r = 16 c .. 16 c + 15, i.e. bytes 32 c .. 32 c + 31 of every
+//            128-byte row of the frame (1024 rows): 32 KB of input per CTA, copied asynchronously (cp.async,
+//            word-swizzled so that the stride-32-byte reads of a branch are conflict-free).  Warp w runs the
+//            32x32 register transform (fft1024_warp.cuh) on branches 2 w and 2 w + 1, multiplies by W_N^(r k)
+//            and PUSHES Z[r][k] straight from its registers into the shared memory of the CTA that owns
+//            column k (k / 256) with st.async, whose completion bytes are counted by that CTA's mbarrier:
+//            no staging, no cluster-wide barrier, 96 of every 128 KB cross the SM-to-SM network.
+//   phase 2  CTA d holds Z[0..63][256 d .. 256 d + 255] (128 KB); thread t loads column 256 d + t (64 LDS.64),
+//            hands the buffer back to the four producers (remote mbarrier arrive) and runs the 64-point
+//            transform in registers, |X|^2, dB / power / u8, 128-byte coalesced streaming stores.
+// The next frame's input is fetched while phase 2 runs; with 50 % overlap only the new half is fetched (the two
+// 16 KB half buffers alternate roles).  Arithmetic per frame is that of spectrum64k.cu instruction for
+// instruction (spectrum.c:15-58, cbb_main.c:112-128), so the two kernels agree bit for bit.
+#include "b200_common.cuh"
+#include "fft1024_warp.cuh"
+#include "spectrum_kernels.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int N64K = 65536;
+constexpr int CL = 4;                                  // CTAs per cluster
+constexpr int C64_THREADS = 256;                       // 8 warps: 16 branches = 2 per warp, 256 columns = 1 per thread
+constexpr int C64_WARPS = 8;
+constexpr int C64_Z_BYTES = 64 * 256 * 8;              // Z[64][256] complex
+constexpr int C64_HALF_BYTES = 512 * 32;               // half a frame's rows, this CTA's 32 bytes of each
+constexpr int C64_XCH_BYTES = 32 * 32 * 8;             // per warp, unpadded, 16-byte granules XOR-swizzled
+constexpr int C64_OFF_IN = C64_Z_BYTES;
+constexpr int C64_OFF_XCH = C64_OFF_IN + 2 * C64_HALF_BYTES;
+constexpr int C64_OFF_BAR = C64_OFF_XCH + C64_WARPS * C64_XCH_BYTES;
+constexpr int C64_SMEM = C64_OFF_BAR + 64;
+static_assert(C64_SMEM <= 232448, "more shared memory than a CTA may have on sm_100");
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_count_x()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `local_smem_addr` in the shared memory of CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+// 8-byte store into a (possibly remote) CTA's shared memory; the destination's mbarrier counts its bytes
+__device__ __forceinline__ void st_async_b64(uint32_t dst_cluster_addr, c64 v, uint32_t bar_cluster_addr)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst_cluster_addr),
+                 "l"(v), "r"(bar_cluster_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst_smem, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+// this thread's earlier cp.async copies arrive on `bar` when they have landed (the count is not raised)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <bool WINDOW>
+__global__ void __launch_bounds__(C64_THREADS, 1) spectrum64k_cluster_kernel(const SpecParams p, const Spec64kExtra x)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const uint32_t rank = cluster_ctarank();
+
+    const c64* Zl = reinterpret_cast<const c64*>(smem);                       // Z[64][256], this CTA's columns
+    uint8_t* inbuf = smem + C64_OFF_IN;                                       // two half buffers [512 rows][8 words]
+    uint8_t* xch = smem + C64_OFF_XCH + warp * C64_XCH_BYTES;
+    uint64_t* in_full = reinterpret_cast<uint64_t*>(smem + C64_OFF_BAR);      // [2], one per half buffer
+    uint64_t* in_empty = in_full + 2;
+    uint64_t* z_full = in_full + 3;
+    uint64_t* z_free = in_full + 4;
+
+    if (tid == 0) {
+        mbar_init(&in_full[0], C64_THREADS);
+        mbar_init(&in_full[1], C64_THREADS);
+        mbar_init(in_empty, C64_WARPS);
+        mbar_init(z_full, 1);
+        mbar_init(z_free, CL * C64_WARPS);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // a cluster takes a CONTIGUOUS run of (stream, row) items, so that with hop = N/2 consecutive frames
+    // share half their rows
+    const int64_t total = (int64_t) p.n_streams * p.n_rows;
+    const int64_t per_cluster = (total + cluster_count_x() - 1) / cluster_count_x();
+    const int64_t item_begin = (int64_t) cluster_id_x() * per_cluster;
+    const int64_t item_end = item_begin + per_cluster < total ? item_begin + per_cluster : total;
+    const uint32_t n_mine = item_begin < item_end ? (uint32_t) (item_end - item_begin) : 0;
+
+    if (tid == 0 && n_mine > 0) mbar_arrive_expect_tx(z_full, C64_Z_BYTES);
+    cluster_sync_all();          // every CTA's barriers exist before anything remote is sent
+
+    uint32_t z_dst[CL], zfull_dst[CL], zfree_dst[CL];
+#pragma unroll
+    for (int d = 0; d < CL; ++d) {
+        z_dst[d] = map_to_rank(smem_u32(smem), d) + lane * 8;
+        zfull_dst[d] = map_to_rank(smem_u32(z_full), d);
+        zfree_dst[d] = map_to_rank(smem_u32(z_free), d);
+    }
+
+    auto frame_of = [&](uint32_t it) {
+        const int64_t item = item_begin + it;
+        const int64_t s = item / p.n_rows;
+        const int64_t row = item - s * p.n_rows;
+        return p.iq + s * p.stream_stride_bytes + 2 * row * p.row_hop;
+    };
+    // copy half a frame (512 rows starting at `src_rows`, this CTA's 32 bytes of each) into half buffer hb:
+    // word w of row m lands at word 8 m + (w ^ ((m >> 2) & 7)); with m = (tid >> 3) + 32 i the swizzle is the
+    // warp index
+    const uint32_t in_dst0 = smem_u32(inbuf) + 32 * (tid >> 3) + 4 * ((tid & 7) ^ warp);
+    const int in_src0 = 128 * (tid >> 3) + 32 * (int) rank + 4 * (tid & 7);
+    auto fetch_half = [&](const uint8_t* src_rows, int hb) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cp_async_4(in_dst0 + hb * C64_HALF_BYTES + 1024 * i, src_rows + in_src0 + 4096 * i);
+        cp_async_arrive(&in_full[hb]);
+    };
+
+    // the half buffer holding rows 0..511 of the current frame, the global rows behind the other one, and how many
+    // fetches each buffer has seen (for the barrier parity)
+    int lo_buf = 0;
+    const uint8_t* held_hi = nullptr;
+    uint32_t n_fetch0 = 0, n_fetch1 = 0;
+    if (n_mine > 0) {
+        const uint8_t* f0 = frame_of(0);
+        fetch_half(f0, 0);
+        fetch_half(f0 + N64K, 1);
+        held_hi = f0 + N64K;
+        n_fetch0 = n_fetch1 = 1;
+    }
+
+    const float dboff = p.db_offset - 16.0f * DB_PER_LOG2;
+    const int sw_in = (lane >> 2) & 7;
+
+    for (uint32_t it = 0; it < n_mine; ++it) {
+        const size_t row_base = (size_t) (item_begin + it) * N64K;
+        const int hi_buf = lo_buf ^ 1;
+
+        // ---- phase 1: branches 16 rank + 2 warp, + 1 ----
+        mbar_wait(&in_full[0], (n_fetch0 - 1) & 1);
+        mbar_wait(&in_full[1], (n_fetch1 - 1) & 1);
+        float2 tw[32];
+        fft1024_load_twiddles(p.twiddle, lane, tw);
+#pragma unroll 1
+        for (int jb = 0; jb < 2; ++jb) {
+            const int rl = 2 * warp + jb;                   // branch within this CTA
+            const int r = 16 * (int) rank + rl;
+            c64 a[32];
+            {
+                // Hann window of sample 64*(32*n1 + lane) + r without a table:
+                //   w = 1/2 - 1/2 cos(2 pi n1 / 32 + phi),  phi = 2 pi (64 lane + r) / 65536
+                float cphi = 1.0f, sphi = 0.0f;
+                if (WINDOW) sincospif((float) (64 * lane + r) * (1.0f / 32768.0f), &sphi, &cphi);
+                const c64 bias1 = cpack(8421376.0f, 8421376.0f);        // 2^23 + 256 * 128
+                const int col = (((rl >> 1) ^ sw_in) << 2) + ((rl & 1) << 1);
+                const uint8_t* lo = inbuf + lo_buf * C64_HALF_BYTES + 32 * lane + col;
+                const uint8_t* hi = inbuf + hi_buf * C64_HALF_BYTES + 32 * lane + col;
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    const uint32_t v = *reinterpret_cast<const uint16_t*>((n1 < 16 ? lo : hi) + 1024 * (n1 & 15));
+                    const int q = bitrev<32>(n1);
+                    a[q] = cpack(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7504)),
+                                 __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7514)));
+                    if (WINDOW) {
+                        const float w = fmaf(0.5f * sin32(n1), sphi, fmaf(-0.5f * cos32(n1), cphi, 0.5f));
+                        a[q] = cmul2(csub(a[q], bias1), cpack(w, w));
+                    }
+                }
+            }
+            if (jb == 1) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(in_empty);       // this warp is done with the frame's input bytes
+            }
+            fft1024_pass1<!WINDOW>(a);
+            // transpose through the warp's tile: element [k1][n2] sits in 16-byte granule (n2 >> 1) ^ (k1 & 7) of row k1
+            __syncwarp();
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) {
+                float re, im;
+                cunpack(a[k1], re, im);
+                *reinterpret_cast<float2*>(xch + 256 * k1 + ((((lane >> 1) ^ (k1 & 7)) << 4) | ((lane & 1) << 3))) =
+                    make_float2(re, im);
+            }
+            __syncwarp();
+            c64 b[32];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const ulonglong2 v =
+                    *reinterpret_cast<const ulonglong2*>(xch + 256 * lane + 128 * (m >> 3) + (((m & 7) ^ (lane & 7)) << 4));
+                b[bitrev<32>(2 * m)] = v.x;
+                b[bitrev<32>(2 * m + 1)] = v.y;
+            }
+            fft_dit32<true>(b, tw);
+            // W_N^(r k) F_r[k]: all 32 table loads are issued before the first product (the st.async below are
+            // volatile, so inside the push loop every load would be waited for on its own: measured, 56 % of all
+            // stall samples)
+            const float2* twr = x.twiddle_rk + r * 1024 + lane;
+            if (r > 0) {
+                float2 w[32];
+#pragma unroll
+                for (int k2 = 0; k2 < 32; ++k2) w[k2] = __ldg(twr + 32 * k2);
+#pragma unroll
+                for (int k2 = 0; k2 < 32; ++k2) b[k2] = cmul(b[k2], w[k2].x, w[k2].y);
+            }
+            // the previous frame's Z must have been read by all four consumers before it is overwritten
+            if (jb == 0 && it > 0) mbar_wait_cluster(z_free, (it - 1) & 1);
+#pragma unroll
+            for (int k2 = 0; k2 < 32; ++k2) {
+                const int d = k2 >> 3;
+                st_async_b64(z_dst[d] + (uint32_t) ((r * 256 + (k2 & 7) * 32) * 8), b[k2], zfull_dst[d]);
+            }
+        }
+
+        // ---- the next frame's input, while phase 2 runs ----
+        if (it + 1 < n_mine) {
+            mbar_wait(in_empty, it & 1);                   // all eight warps have their samples in registers
+            const uint8_t* nf = frame_of(it + 1);
+            if (nf == held_hi) {                            // hop = N/2: the old second half is the new first half
+                fetch_half(nf + N64K, lo_buf);
+                if (lo_buf) ++n_fetch1;
+                else ++n_fetch0;
+                lo_buf = hi_buf;
+            } else {
+                fetch_half(nf, 0);
+                fetch_half(nf + N64K, 1);
+                ++n_fetch0;
+                ++n_fetch1;
+                lo_buf = 0;
+            }
+            held_hi = nf + N64K;
+        }
+
+        // ---- phase 2: column 256 rank + tid ----
+        mbar_wait(z_full, it & 1);
+        c64 z[64];
+#pragma unroll
+        for (int r = 0; r < 64; ++r) z[bitrev<64>(r)] = Zl[r * 256 + tid];
+        if (tid == 0 && it + 1 < n_mine) mbar_arrive_expect_tx(z_full, C64_Z_BYTES);
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int d = 0; d < CL; ++d) mbar_arrive_remote(zfree_dst[d]);
+        }
+        fft_dit64(z);
+        const int k = 256 * (int) rank + tid;
+#pragma unroll
+        for (int q = 0; q < 64; ++q) {
+            float re, im;
+            cunpack(z[q], re, im);
+            const float pw = fmaf(re, re, im * im);
+            const float db = fmaf(DB_PER_LOG2, lg2_ftz(pw), dboff);
+            // fftshift (spectrum.c:25); bin N-1 also supplies the DC position (spectrum.c:30-33 with K = 1)
+            const bool last = (k == 1023 && q == 63);
+            const bool first = (k == 0 && q == 0);
+            const size_t at = row_base + (size_t) (1024 * ((q + 32) & 63) + k);
+            if (!first) {
+                if (p.db) __stcs(p.db + at, db);
+                if (p.power) __stcs(p.power + at, pw * FFT1024_POWER_SCALE);
+                if (p.db_u8) {
+                    int m = __float2int_rz(db);
+                    m = m < 0 ? 0 : (m > 255 ? 255 : m);
+                    p.db_u8[at] = (uint8_t) m;
+                }
+            }
+            if (last) {
+                const size_t dc = row_base + N64K / 2;
+                if (p.db) __stcs(p.db + dc, db);
+                if (p.power) __stcs(p.power + dc, pw * FFT1024_POWER_SCALE);
+                if (p.db_u8) {
+                    int m = __float2int_rz(db);
+                    m = m < 0 ? 0 : (m > 255 ? 255 : m);
+                    p.db_u8[dc] = (uint8_t) m;
+                }
+            }
+        }
+    }
+    cluster_sync_all();          // nobody leaves while a neighbour may still signal its barriers
+}
+
+}  // namespace
+
+// Largest number of four-CTA clusters the device runs at once for this kernel (0: cluster launch unavailable).
+static int cluster_capacity(const void* kern)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL * 64, 1, 1);
+    cfg.blockDim = dim3(C64_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = C64_SMEM;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// K = 1 rows only; returns B200_ERR_ARG (without an error message) if the plan needs the scratch kernel instead
+int launch_spectrum64k_cluster(const SpecParams& p, const Spec64kExtra& x, cudaStream_t stream)
+{
+    const int64_t total = (int64_t) p.n_streams * p.n_rows;
+    if (total == 0) return B200_OK;
+    auto kern = p.window ? spectrum64k_cluster_kernel<true> : spectrum64k_cluster_kernel<false>;
+    if (int rc = ensure_dynamic_smem((const void*) kern, C64_SMEM)) return rc;
+    static int capacity[64][2];
+    static bool known[64][2];
+    int dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    const int wi = p.window ? 1 : 0;
+    if (dev < 64 && !known[dev][wi]) {
+        capacity[dev][wi] = cluster_capacity((const void*) kern);
+        known[dev][wi] = true;
+    }
+    int64_t clusters = dev < 64 ? capacity[dev][wi] : cluster_capacity((const void*) kern);
+    if (clusters <= 0) {
+        set_error("spectrum 65536: the device does not co-schedule clusters of %d CTAs with %d bytes of shared memory", CL,
+                  C64_SMEM);
+        return B200_ERR_CUDA;
+    }
+    if (clusters > total) clusters = total;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) (CL * clusters), 1, 1);
+    cfg.blockDim = dim3(C64_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = C64_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p, x));
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+}  // namespace b200

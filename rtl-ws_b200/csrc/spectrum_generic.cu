@@ -159,15 +159,18 @@ __global__ void __launch_bounds__(GEN_THREADS) spectrum_generic_kernel(const Spe
     }
 }
 
-float2* g_scratch = nullptr;
-float* g_acc_scratch = nullptr;
-size_t g_scratch_elems = 0;
-int g_scratch_ctas = 0;
-
 }  // namespace
 
-// kind: 0 = cmplx_u8, 1 = cmplx_s32, 2 = real f32
-int launch_spectrum_generic(const SpecParams& p, int N, int kind, cudaStream_t stream)
+// CTAs the N > 8192 form runs (and the number of per-CTA work arrays the caller must provide)
+int spectrum_generic_scratch_ctas()
+{
+    return sm_count() * 2;
+}
+
+// kind: 0 = cmplx_u8, 1 = cmplx_s32, 2 = real f32.  N > 8192 works out of global memory: `scratch` is
+// [scratch_ctas][2][N] complex and `acc_scratch` [scratch_ctas][N], owned by the caller's plan (one exec at a time).
+int launch_spectrum_generic(const SpecParams& p, int N, int kind, float2* scratch, float* acc_scratch, int scratch_ctas,
+                            cudaStream_t stream)
 {
     if (N < 16 || N > 65536 || (N & (N - 1)) != 0) {
         set_error("spectrum: N = %d is not a power of two in [16, 65536]", N);
@@ -178,28 +181,18 @@ int launch_spectrum_generic(const SpecParams& p, int N, int kind, cudaStream_t s
     const int sample_bytes = kind == IN_CU8 ? 2 : (kind == IN_CS32 ? 8 : 4);
     int grid;
     int smem = 0;
-    float2* scratch = nullptr;
-    float* acc_scratch = nullptr;
     if (N <= GEN_SMEM_MAX_N) {
         smem = 2 * N * 8 + N * 4;
         const int per_sm = smem > 113 * 1024 ? 1 : (smem > 56 * 1024 ? 2 : 3);
         grid = sm_count() * per_sm;
+        scratch = nullptr;
+        acc_scratch = nullptr;
     } else {
-        grid = sm_count() * 2;
-        const size_t need = (size_t) grid * 2 * N;
-        if (g_scratch_elems < need || g_scratch_ctas < grid) {
-            if (g_scratch) cudaFree(g_scratch);
-            if (g_acc_scratch) cudaFree(g_acc_scratch);
-            g_scratch = nullptr;
-            g_acc_scratch = nullptr;
-            g_scratch_elems = 0;
-            B200_CUDA_TRY(cudaMalloc(&g_scratch, need * sizeof(float2)));
-            B200_CUDA_TRY(cudaMalloc(&g_acc_scratch, (size_t) grid * N * sizeof(float)));
-            g_scratch_elems = need;
-            g_scratch_ctas = grid;
+        if (scratch == nullptr || acc_scratch == nullptr || scratch_ctas <= 0) {
+            set_error("spectrum: N = %d needs the plan's scratch", N);
+            return B200_ERR_ARG;
         }
-        scratch = g_scratch;
-        acc_scratch = g_acc_scratch;
+        grid = scratch_ctas;
     }
     if (grid > total) grid = (int) total;
     auto kern = kind == IN_CU8 ? spectrum_generic_kernel<IN_CU8>

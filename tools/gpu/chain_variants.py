@@ -14,7 +14,7 @@ import torch  # noqa: E402
 import __graft_entry__ as graft  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--variants", default="0,1,2,3,4,5,6,7")
+ap.add_argument("--variants", default="0,1,2,3,4,5,6")
 ap.add_argument("--streams", type=int, default=256)
 ap.add_argument("--samples", type=int, default=5120 * 1600)
 ap.add_argument("--long-reps", type=int, default=300)

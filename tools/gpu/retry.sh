@@ -1,0 +1,9 @@
+#!/bin/bash
+# retry.sh <timeout> <command...>: gpurun with retries while the pod answers busy (exit 3 / transient)
+T=$1; shift
+for i in $(seq 1 20); do
+  out=$(/usr/local/graft/bin/gpurun --timeout $T -- "$@" 2>&1); rc=$?
+  if echo "$out" | grep -q "status=transient\|nothing was charged"; then sleep 120; continue; fi
+  echo "$out"; exit $rc
+done
+echo "gave up after 20 tries"; exit 3
