@@ -294,6 +294,14 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
             }
         bool ok = cudaMalloc((void**) &pl->x64.twiddle_rk, sizeof(float2) * trk.size()) == cudaSuccess &&
                   cudaMemcpy((void*) pl->x64.twiddle_rk, trk.data(), sizeof(float2) * trk.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        std::vector<float2> t32((size_t) 32 * 32);
+        for (int n2 = 0; n2 < 32; ++n2)
+            for (int k1 = 0; k1 < 32; ++k1) {
+                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double) (n2 * k1) / 1024.0L;
+                t32[(size_t) n2 * 32 + k1] = make_float2((float) cosl(a), (float) sinl(a));
+            }
+        ok = ok && cudaMalloc((void**) &pl->x64.twiddle_32x32, sizeof(float2) * t32.size()) == cudaSuccess &&
+             cudaMemcpy((void*) pl->x64.twiddle_32x32, t32.data(), sizeof(float2) * t32.size(), cudaMemcpyHostToDevice) == cudaSuccess;
         pl->x64.scratch_ctas = sm_count();
         ok = ok && cudaMalloc((void**) &pl->x64.scratch, sizeof(float2) * 65536 * (size_t) pl->x64.scratch_ctas) == cudaSuccess;
         if (ok && K > 1) ok = cudaMalloc((void**) &pl->x64.acc, sizeof(float) * 65536 * (size_t) pl->x64.scratch_ctas) == cudaSuccess;
@@ -315,6 +323,7 @@ void b200_spectrum_plan_destroy(b200_spectrum_plan* plan)
     if (plan->d_twiddle_4k) cudaFree(plan->d_twiddle_4k);
     if (plan->d_window) cudaFree(plan->d_window);
     if (plan->x64.twiddle_rk) cudaFree((void*) plan->x64.twiddle_rk);
+    if (plan->x64.twiddle_32x32) cudaFree((void*) plan->x64.twiddle_32x32);
     if (plan->x64.scratch) cudaFree(plan->x64.scratch);
     if (plan->x64.acc) cudaFree(plan->x64.acc);
     if (plan->gen_scratch) cudaFree(plan->gen_scratch);
@@ -378,11 +387,10 @@ static int spectrum_exec_kind(b200_spectrum_plan* plan, const void* d_in, int64_
         p.twiddle = plan->d_twiddle1024;
         p.twiddle_n = plan->N == 65536 ? plan->d_twiddle : plan->d_twiddle_rk;
         if (plan->N == 65536) {
-            // K = 1 rows run on four-CTA clusters with Z in distributed shared memory (spectrum64k_cluster.cu);
-            // K > 1 rows keep the scratch kernel.  B200_S64K_SCRATCH=1 forces the scratch kernel (A/B measurements).
-            const char* env = getenv("B200_S64K_SCRATCH");
-            const bool force_scratch = env != nullptr && atoi(env) != 0;
-            if (plan->K == 1 && !force_scratch) return launch_spectrum64k_cluster(p, plan->x64, stream);
+            // B200_S64K_CLUSTER=1 selects the four-CTA cluster kernel (Z in distributed shared memory, K = 1 rows;
+            // spectrum64k_cluster.cu): DRAM traffic 1.0x algorithmic but 90 vs 125 Gsamples/s, so it is not the default.
+            const char* env = getenv("B200_S64K_CLUSTER");
+            if (plan->K == 1 && env != nullptr && atoi(env) != 0) return launch_spectrum64k_cluster(p, plan->x64, stream);
             return with_plan_scratch(plan, stream, [&] { return launch_spectrum64k(p, plan->x64, stream); });
         }
         if (plan->N == 4096) {

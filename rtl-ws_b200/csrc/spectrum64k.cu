@@ -69,37 +69,42 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
     const int64_t per_cta = (total + gridDim.x - 1) / gridDim.x;
     const int64_t item_begin = (int64_t) blockIdx.x * per_cta;
     const int64_t item_end = item_begin + per_cta < total ? item_begin + per_cta : total;
-    const uint8_t* resident = nullptr;      // global address of the frame now in shared memory
     int flip = 0;
 
-    for (int64_t item = item_begin; item < item_end; ++item) {
+    // frames in the order this CTA transforms them: seq = (item - item_begin) * K + j
+    const int64_t n_seq = item_begin < item_end ? (item_end - item_begin) * K : 0;
+    auto frame_of = [&](int64_t seq) {
+        const int64_t item = item_begin + seq / K;
+        const int j = (int) (seq - (seq / K) * K);
         const int64_t s = item / p.n_rows;
         const int64_t row = item - s * p.n_rows;
+        return p.iq + s * p.stream_stride_bytes + 2 * (row * p.row_hop + (int64_t) j * p.hop);
+    };
+    // 0. frame -> shared memory with 4-byte cp.async copies (LDGSTS: no registers, nothing waits), rows word-swizzled
+    //    by (m mod 32): word w of logical row m lands in word w ^ (m & 31) of physical row m ^ flip_.  Thread t
+    //    copies word (t & 31) of rows (t >> 5) + 8 i.  The fetch of frame seq + 1 is issued as soon as phase 1 of frame
+    //    seq is over (its bytes are dead then) and lands while phase 2 runs.
+    auto fetch = [&](const uint8_t* frame, int flip_, bool half) {
+        const uint32_t dst0 = smem_u32(frame32);
+        const uint8_t* src0 = frame + 4 * tid;
+#pragma unroll 8
+        for (int i = half ? 64 : 0; i < 128; ++i) {
+            const int m = warp + 8 * i;
+            const uint32_t dst = dst0 + (uint32_t) ((m ^ flip_) * 128 + 4 * (lane ^ (m & 31)));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src0 + 1024 * i) : "memory");
+        }
+    };
+    if (n_seq > 0) fetch(frame_of(0), 0, false);
+    const uint8_t* resident = n_seq > 0 ? frame_of(0) : nullptr;      // global address of the frame in shared memory
+
+    for (int64_t item = item_begin; item < item_end; ++item) {
         const size_t row_base = (size_t) item * N64K;
         float dcacc = 0.0f;
 
         for (int j = 0; j < K; ++j) {
-            // ---- 0. frame -> shared memory, rows word-swizzled by (m mod 32) ----
-            const uint8_t* frame = p.iq + s * p.stream_stride_bytes + 2 * (row * p.row_hop + (int64_t) j * p.hop);
-            const bool half = resident != nullptr && frame == resident + S64_FRAME_BYTES / 2;
-            if (half) flip ^= 512;          // the old second half is the new first half
-            else flip = 0;
-            resident = frame;
-            const uint4* src = reinterpret_cast<const uint4*>(frame);
-            const int i0 = half ? S64_FRAME_BYTES / 32 : 0;
-#pragma unroll 4
-            for (int i = i0 + tid; i < S64_FRAME_BYTES / 16; i += S64_THREADS) {
-                const uint4 v = __ldg(src + i);
-                const int m = i >> 3;
-                const int w0 = (i & 7) * 4;
-                uint32_t* dst = frame32 + (m ^ flip) * 32;
-                const int sw = m & 31;
-                dst[(w0 + 0) ^ sw] = v.x;
-                dst[(w0 + 1) ^ sw] = v.y;
-                dst[(w0 + 2) ^ sw] = v.z;
-                dst[(w0 + 3) ^ sw] = v.w;
-            }
-            __syncthreads();
+            const int64_t seq = (item - item_begin) * K + j;
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();          // the frame is in shared memory; Z and dc_slot of the previous frame are free
 
             // ---- 1. polyphase branches r = warp, warp + 8, ...  (the lane-private inter-pass twiddles
             //         are re-read per frame so that they are not live during phase 2) ----
@@ -148,6 +153,13 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
                 }
             }
             __syncthreads();          // Z[.][.] of this frame is complete and visible to the CTA
+            if (seq + 1 < n_seq) {
+                const uint8_t* next = frame_of(seq + 1);
+                const bool half = (next == resident + S64_FRAME_BYTES / 2);   // the old second half is the new first half
+                flip = half ? flip ^ 512 : 0;
+                resident = next;
+                fetch(next, flip, half);
+            }
 
             // ---- 2. 64-point transforms across r for k = tid + 320 g ----
             for (int g = 0; g < (1024 + S64_THREADS - 1) / S64_THREADS; ++g) {
@@ -194,6 +206,10 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
 
 }  // namespace
 
+// Tried and dropped (round 2, measured): asking the L2 to keep the Z scratch -- an access-policy window with the
+// persisting property over the 74 MB, backed by a set-aside of the same size.  DRAM writes went UP (6.9 -> 11.9 GB per
+// 524 M samples: what is left of the L2 no longer absorbs the streaming rows) and the kernel lost 3 % (123 -> 119
+// Gsamples/s).  The four-CTA cluster kernel (spectrum64k_cluster.cu) removes the scratch altogether.
 int launch_spectrum64k(const SpecParams& p, const Spec64kExtra& x, cudaStream_t stream)
 {
     const int64_t total = (int64_t) p.n_streams * p.n_rows;

@@ -29,8 +29,8 @@ namespace {
 
 constexpr int N64K = 65536;
 constexpr int CL = 4;                                  // CTAs per cluster
-constexpr int C64_THREADS = 256;                       // 8 warps: 16 branches = 2 per warp, 256 columns = 1 per thread
-constexpr int C64_WARPS = 8;
+constexpr int C64_THREADS = 384;                       // 8 producer + 4 consumer warps (see the kernel)
+constexpr int C64_WARPS = 8;                           // warps with an exchange tile (the producers)
 constexpr int C64_Z_BYTES = 64 * 256 * 8;              // Z[64][256] complex
 constexpr int C64_HALF_BYTES = 512 * 32;               // half a frame's rows, this CTA's 32 bytes of each
 constexpr int C64_XCH_BYTES = 32 * 32 * 8;             // per warp, unpadded, 16-byte granules XOR-swizzled
@@ -76,22 +76,12 @@ __device__ __forceinline__ void st_async_b64(uint32_t dst_cluster_addr, c64 v, u
                  "l"(v), "r"(bar_cluster_addr)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr)
+// Arrive on a (possibly remote) CTA's mbarrier WITHOUT release semantics: a release at cluster scope is a
+// MEMBAR.ALL.GPU in SASS, which waits for every global store the warp has in flight (64 spectrum stores per run:
+// measured, 24 % of the consumers' stall samples).  The callers order what has to be ordered by a data dependency.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t bar_cluster_addr)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cp_async_4(uint32_t dst_smem, const void* src)
 {
@@ -102,6 +92,42 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar)
 {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+// Warp roles.  Phase 2 needs 64 complex values per thread (200+ registers), phase 1 about 150, and eight warps of
+// the larger size are all an SM holds -- two per scheduler, not enough to hide the latencies of either phase (the
+// symmetric first version of this kernel: 33 % of issue slots used, 98 Gsamples/s).  So the roles are split over
+// twelve warps: warps 0-7 PRODUCE (phase 1, two branches per warp and frame), warps 8-11 CONSUME (phase 2, two runs
+// of 32 columns per warp and frame) and fetch the input.  Producers work on frame f + 1 while consumers finish
+// frame f.  With the inter-pass twiddles read from an L1-resident table instead of 62 registers, either role fits
+// the 168 registers a 384-thread CTA leaves per thread (ptxas: 142), so no setmaxnreg is needed.
+constexpr int C64_PRODUCERS = 8;
+constexpr int C64_CONSUMERS = 4;
+
+// Where the two halves of a frame's rows live.  Both roles replay the same sequence of frame addresses, so they
+// agree on buffers and barrier parities without talking to each other.
+struct InputState {
+    int lo_buf = 0;                     // half buffer with rows 0..511 of the current frame
+    const uint8_t* held_hi = nullptr;   // global rows behind the other half buffer
+    uint32_t n_fetch0 = 0, n_fetch1 = 0;
+    // advance to the frame at `nf`; returns true if only the new second half has to be fetched (into `fetch_buf`)
+    __device__ __forceinline__ bool step(const uint8_t* nf, int& fetch_buf)
+    {
+        const bool half = (nf == held_hi);          // hop = N/2: the old second half is the new first half
+        if (half) {
+            fetch_buf = lo_buf;
+            if (lo_buf) ++n_fetch1;
+            else ++n_fetch0;
+            lo_buf ^= 1;
+        } else {
+            fetch_buf = -1;
+            ++n_fetch0;
+            ++n_fetch1;
+            lo_buf = 0;
+        }
+        held_hi = nf + N64K;
+        return half;
+    }
+};
 
 template <bool WINDOW>
 __global__ void __launch_bounds__(C64_THREADS, 1) spectrum64k_cluster_kernel(const SpecParams p, const Spec64kExtra x)
@@ -114,18 +140,18 @@ __global__ void __launch_bounds__(C64_THREADS, 1) spectrum64k_cluster_kernel(con
 
     const c64* Zl = reinterpret_cast<const c64*>(smem);                       // Z[64][256], this CTA's columns
     uint8_t* inbuf = smem + C64_OFF_IN;                                       // two half buffers [512 rows][8 words]
-    uint8_t* xch = smem + C64_OFF_XCH + warp * C64_XCH_BYTES;
     uint64_t* in_full = reinterpret_cast<uint64_t*>(smem + C64_OFF_BAR);      // [2], one per half buffer
     uint64_t* in_empty = in_full + 2;
     uint64_t* z_full = in_full + 3;
-    uint64_t* z_free = in_full + 4;
+    uint64_t* z_free = in_full + 4;                                           // [2]: columns of consumer run 0 / run 1
 
     if (tid == 0) {
-        mbar_init(&in_full[0], C64_THREADS);
-        mbar_init(&in_full[1], C64_THREADS);
-        mbar_init(in_empty, C64_WARPS);
+        mbar_init(&in_full[0], 32 * C64_CONSUMERS);
+        mbar_init(&in_full[1], 32 * C64_CONSUMERS);
+        mbar_init(in_empty, C64_PRODUCERS);
         mbar_init(z_full, 1);
-        mbar_init(z_free, CL * C64_WARPS);
+        mbar_init(&z_free[0], CL * C64_CONSUMERS);
+        mbar_init(&z_free[1], CL * C64_CONSUMERS);
         fence_mbar_init();
     }
     __syncthreads();
@@ -141,186 +167,225 @@ __global__ void __launch_bounds__(C64_THREADS, 1) spectrum64k_cluster_kernel(con
     if (tid == 0 && n_mine > 0) mbar_arrive_expect_tx(z_full, C64_Z_BYTES);
     cluster_sync_all();          // every CTA's barriers exist before anything remote is sent
 
-    uint32_t z_dst[CL], zfull_dst[CL], zfree_dst[CL];
-#pragma unroll
-    for (int d = 0; d < CL; ++d) {
-        z_dst[d] = map_to_rank(smem_u32(smem), d) + lane * 8;
-        zfull_dst[d] = map_to_rank(smem_u32(z_full), d);
-        zfree_dst[d] = map_to_rank(smem_u32(z_free), d);
-    }
-
     auto frame_of = [&](uint32_t it) {
         const int64_t item = item_begin + it;
         const int64_t s = item / p.n_rows;
         const int64_t row = item - s * p.n_rows;
         return p.iq + s * p.stream_stride_bytes + 2 * row * p.row_hop;
     };
-    // copy half a frame (512 rows starting at `src_rows`, this CTA's 32 bytes of each) into half buffer hb:
-    // word w of row m lands at word 8 m + (w ^ ((m >> 2) & 7)); with m = (tid >> 3) + 32 i the swizzle is the
-    // warp index
-    const uint32_t in_dst0 = smem_u32(inbuf) + 32 * (tid >> 3) + 4 * ((tid & 7) ^ warp);
-    const int in_src0 = 128 * (tid >> 3) + 32 * (int) rank + 4 * (tid & 7);
-    auto fetch_half = [&](const uint8_t* src_rows, int hb) {
+    InputState in;
+
+    if (warp < C64_PRODUCERS) {
+        // ================================ producers: phase 1 ================================
+        uint8_t* xch = smem + C64_OFF_XCH + warp * C64_XCH_BYTES;
+        uint32_t z_dst[CL], zfull_dst[CL];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) cp_async_4(in_dst0 + hb * C64_HALF_BYTES + 1024 * i, src_rows + in_src0 + 4096 * i);
-        cp_async_arrive(&in_full[hb]);
-    };
+        for (int d = 0; d < CL; ++d) {
+            z_dst[d] = map_to_rank(smem_u32(smem), d) + lane * 8;
+            zfull_dst[d] = map_to_rank(smem_u32(z_full), d);
+        }
+        const int sw_in = (lane >> 2) & 7;
+        const float2* tw_lane = x.twiddle_32x32 + lane;       // [n2][k1] W_1024^(n2 k1), this lane's column (L1-resident)
 
-    // the half buffer holding rows 0..511 of the current frame, the global rows behind the other one, and how many
-    // fetches each buffer has seen (for the barrier parity)
-    int lo_buf = 0;
-    const uint8_t* held_hi = nullptr;
-    uint32_t n_fetch0 = 0, n_fetch1 = 0;
-    if (n_mine > 0) {
-        const uint8_t* f0 = frame_of(0);
-        fetch_half(f0, 0);
-        fetch_half(f0 + N64K, 1);
-        held_hi = f0 + N64K;
-        n_fetch0 = n_fetch1 = 1;
-    }
-
-    const float dboff = p.db_offset - 16.0f * DB_PER_LOG2;
-    const int sw_in = (lane >> 2) & 7;
-
-    for (uint32_t it = 0; it < n_mine; ++it) {
-        const size_t row_base = (size_t) (item_begin + it) * N64K;
-        const int hi_buf = lo_buf ^ 1;
-
-        // ---- phase 1: branches 16 rank + 2 warp, + 1 ----
-        mbar_wait(&in_full[0], (n_fetch0 - 1) & 1);
-        mbar_wait(&in_full[1], (n_fetch1 - 1) & 1);
-        float2 tw[32];
-        fft1024_load_twiddles(p.twiddle, lane, tw);
+        for (uint32_t it = 0; it < n_mine; ++it) {
+            int unused;
+            in.step(frame_of(it), unused);
+            const int lo_buf = in.lo_buf, hi_buf = lo_buf ^ 1;
+            mbar_wait(&in_full[0], (in.n_fetch0 - 1) & 1);
+            mbar_wait(&in_full[1], (in.n_fetch1 - 1) & 1);
+            c64 held[16];                                       // branch A's odd-k2 half, pushed after branch B
 #pragma unroll 1
-        for (int jb = 0; jb < 2; ++jb) {
-            const int rl = 2 * warp + jb;                   // branch within this CTA
-            const int r = 16 * (int) rank + rl;
-            c64 a[32];
-            {
-                // Hann window of sample 64*(32*n1 + lane) + r without a table:
-                //   w = 1/2 - 1/2 cos(2 pi n1 / 32 + phi),  phi = 2 pi (64 lane + r) / 65536
-                float cphi = 1.0f, sphi = 0.0f;
-                if (WINDOW) sincospif((float) (64 * lane + r) * (1.0f / 32768.0f), &sphi, &cphi);
-                const c64 bias1 = cpack(8421376.0f, 8421376.0f);        // 2^23 + 256 * 128
-                const int col = (((rl >> 1) ^ sw_in) << 2) + ((rl & 1) << 1);
-                const uint8_t* lo = inbuf + lo_buf * C64_HALF_BYTES + 32 * lane + col;
-                const uint8_t* hi = inbuf + hi_buf * C64_HALF_BYTES + 32 * lane + col;
+            for (int jb = 0; jb < 2; ++jb) {
+                const int rl = 2 * warp + jb;                   // branch within this CTA
+                const int r = 16 * (int) rank + rl;
+                c64 a[32];
+                {
+                    // Hann window of sample 64*(32*n1 + lane) + r without a table:
+                    //   w = 1/2 - 1/2 cos(2 pi n1 / 32 + phi),  phi = 2 pi (64 lane + r) / 65536
+                    float cphi = 1.0f, sphi = 0.0f;
+                    if (WINDOW) sincospif((float) (64 * lane + r) * (1.0f / 32768.0f), &sphi, &cphi);
+                    const c64 bias1 = cpack(8421376.0f, 8421376.0f);        // 2^23 + 256 * 128
+                    const int col = (((rl >> 1) ^ sw_in) << 2) + ((rl & 1) << 1);
+                    const uint8_t* lo = inbuf + lo_buf * C64_HALF_BYTES + 32 * lane + col;
+                    const uint8_t* hi = inbuf + hi_buf * C64_HALF_BYTES + 32 * lane + col;
 #pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    const uint32_t v = *reinterpret_cast<const uint16_t*>((n1 < 16 ? lo : hi) + 1024 * (n1 & 15));
-                    const int q = bitrev<32>(n1);
-                    a[q] = cpack(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7504)),
-                                 __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7514)));
-                    if (WINDOW) {
-                        const float w = fmaf(0.5f * sin32(n1), sphi, fmaf(-0.5f * cos32(n1), cphi, 0.5f));
-                        a[q] = cmul2(csub(a[q], bias1), cpack(w, w));
+                    for (int n1 = 0; n1 < 32; ++n1) {
+                        const uint32_t v = *reinterpret_cast<const uint16_t*>((n1 < 16 ? lo : hi) + 1024 * (n1 & 15));
+                        const int q = bitrev<32>(n1);
+                        a[q] = cpack(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7504)),
+                                     __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7514)));
+                        if (WINDOW) {
+                            const float w = fmaf(0.5f * sin32(n1), sphi, fmaf(-0.5f * cos32(n1), cphi, 0.5f));
+                            a[q] = cmul2(csub(a[q], bias1), cpack(w, w));
+                        }
                     }
                 }
-            }
-            if (jb == 1) {
+                if (jb == 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(in_empty);       // this warp is done with the frame's input bytes
+                }
+                fft1024_pass1<!WINDOW>(a);
+                // transpose through the warp's tile: element [k1][n2] sits in 16-byte granule (n2 >> 1) ^ (k1 & 7) of row k1
                 __syncwarp();
-                if (lane == 0) mbar_arrive(in_empty);       // this warp is done with the frame's input bytes
-            }
-            fft1024_pass1<!WINDOW>(a);
-            // transpose through the warp's tile: element [k1][n2] sits in 16-byte granule (n2 >> 1) ^ (k1 & 7) of row k1
-            __syncwarp();
 #pragma unroll
-            for (int k1 = 0; k1 < 32; ++k1) {
-                float re, im;
-                cunpack(a[k1], re, im);
-                *reinterpret_cast<float2*>(xch + 256 * k1 + ((((lane >> 1) ^ (k1 & 7)) << 4) | ((lane & 1) << 3))) =
-                    make_float2(re, im);
-            }
-            __syncwarp();
-            c64 b[32];
+                for (int k1 = 0; k1 < 32; ++k1) {
+                    float re, im;
+                    cunpack(a[k1], re, im);
+                    *reinterpret_cast<float2*>(xch + 256 * k1 + ((((lane >> 1) ^ (k1 & 7)) << 4) | ((lane & 1) << 3))) =
+                        make_float2(re, im);
+                }
+                __syncwarp();
+                c64 b[32];
 #pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const ulonglong2 v =
-                    *reinterpret_cast<const ulonglong2*>(xch + 256 * lane + 128 * (m >> 3) + (((m & 7) ^ (lane & 7)) << 4));
-                b[bitrev<32>(2 * m)] = v.x;
-                b[bitrev<32>(2 * m + 1)] = v.y;
-            }
-            fft_dit32<true>(b, tw);
-            // W_N^(r k) F_r[k]: all 32 table loads are issued before the first product (the st.async below are
-            // volatile, so inside the push loop every load would be waited for on its own: measured, 56 % of all
-            // stall samples)
-            const float2* twr = x.twiddle_rk + r * 1024 + lane;
-            if (r > 0) {
-                float2 w[32];
+                for (int m = 0; m < 16; ++m) {
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xch + 256 * lane + 128 * (m >> 3) +
+                                                                               (((m & 7) ^ (lane & 7)) << 4));
+                    b[bitrev<32>(2 * m)] = v.x;
+                    b[bitrev<32>(2 * m + 1)] = v.y;
+                }
+                fft_dit32_pretwiddled_ldg(b, tw_lane);
+                // W_N^(r k) F_r[k]: the table loads of half a row are issued together, ahead of their products (the
+                // st.async below are volatile: inside the push loop every load would be waited for on its own --
+                // measured, 56 % of all stall samples).  ld.global.cg: 128 KB per frame must not sweep the small L1.
+                const float2* twr = x.twiddle_rk + r * 1024 + lane;
+                if (r > 0) {
 #pragma unroll
-                for (int k2 = 0; k2 < 32; ++k2) w[k2] = __ldg(twr + 32 * k2);
+                    for (int h = 0; h < 2; ++h) {
+                        float2 w[16];
 #pragma unroll
-                for (int k2 = 0; k2 < 32; ++k2) b[k2] = cmul(b[k2], w[k2].x, w[k2].y);
-            }
-            // the previous frame's Z must have been read by all four consumers before it is overwritten
-            if (jb == 0 && it > 0) mbar_wait_cluster(z_free, (it - 1) & 1);
+                        for (int k2 = 0; k2 < 16; ++k2) w[k2] = __ldcg(twr + 32 * (16 * h + k2));
 #pragma unroll
-            for (int k2 = 0; k2 < 32; ++k2) {
-                const int d = k2 >> 3;
-                st_async_b64(z_dst[d] + (uint32_t) ((r * 256 + (k2 & 7) * 32) * 8), b[k2], zfull_dst[d]);
+                        for (int k2 = 0; k2 < 16; ++k2) b[16 * h + k2] = cmul(b[16 * h + k2], w[k2].x, w[k2].y);
+                    }
+                }
+                // Z hand-back is split by consumer run: columns with even k2 belong to run 0 of some consumer warp
+                // (read at the very start of its frame), odd k2 to run 1 (read half a frame later).  Branch A pushes
+                // its even half at once and keeps the odd half in registers until branch B is done, so the wait for
+                // the late hand-back never sits between a producer and its next transform.  The consumers' arrives
+                // are release.cluster; nothing they WROTE is read here (what follows are stores that cannot start
+                // before the wait has succeeded), so the waits need no cluster-scope acquire -- which ptxas implements
+                // as CCTL.IVALL after every poll: measured, 27 % of all stall samples and an L1 that never keeps the
+                // twiddle table.
+                auto push = [&](int rr, int k2, c64 v) {
+                    const int d = k2 >> 3;
+                    st_async_b64(z_dst[d] + (uint32_t) ((rr * 256 + (k2 & 7) * 32) * 8), v, zfull_dst[d]);
+                };
+                if (jb == 0) {
+                    if (it > 0) mbar_wait(&z_free[0], (it - 1) & 1);
+#pragma unroll
+                    for (int k2 = 0; k2 < 32; k2 += 2) push(r, k2, b[k2]);
+#pragma unroll
+                    for (int k2 = 1; k2 < 32; k2 += 2) held[k2 >> 1] = b[k2];
+                } else {
+                    if (it > 0) mbar_wait(&z_free[1], (it - 1) & 1);
+#pragma unroll
+                    for (int k2 = 1; k2 < 32; k2 += 2) push(r - 1, k2, held[k2 >> 1]);
+#pragma unroll
+                    for (int k2 = 0; k2 < 32; ++k2) push(r, k2, b[k2]);
+                }
             }
         }
-
-        // ---- the next frame's input, while phase 2 runs ----
-        if (it + 1 < n_mine) {
-            mbar_wait(in_empty, it & 1);                   // all eight warps have their samples in registers
-            const uint8_t* nf = frame_of(it + 1);
-            if (nf == held_hi) {                            // hop = N/2: the old second half is the new first half
-                fetch_half(nf + N64K, lo_buf);
-                if (lo_buf) ++n_fetch1;
-                else ++n_fetch0;
-                lo_buf = hi_buf;
+    } else {
+        // ================================ consumers: input fetch + phase 2 ================================
+        const int ct = tid - 32 * C64_PRODUCERS;             // 0..127
+        const int cw = ct >> 5;
+        uint32_t zfree_dst[CL];                               // z_free[0] of every CTA of the cluster (z_free[1] is 8 bytes on)
+#pragma unroll
+        for (int d = 0; d < CL; ++d) zfree_dst[d] = map_to_rank(smem_u32(z_free), d);
+        // copy half a frame (512 rows starting at `src_rows`, this CTA's 32 bytes of each) into half buffer hb: word w
+        // of row m lands at word 8 m + (w ^ ((m >> 2) & 7)).  Thread ct takes word ct & 7 of rows (ct >> 3) + 16 i, whose
+        // swizzle is cw for even i and cw + 4 for odd i.
+        const uint32_t in_dst_even = smem_u32(inbuf) + 32 * (ct >> 3) + 4 * ((ct & 7) ^ cw);
+        const uint32_t in_dst_odd = smem_u32(inbuf) + 32 * (ct >> 3) + 4 * ((ct & 7) ^ cw ^ 4);
+        const int in_src0 = 128 * (ct >> 3) + 32 * (int) rank + 4 * (ct & 7);
+        auto fetch_half = [&](const uint8_t* src_rows, int hb) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                cp_async_4(((i & 1) ? in_dst_odd : in_dst_even) + hb * C64_HALF_BYTES + 512 * i, src_rows + in_src0 + 2048 * i);
+            cp_async_arrive(&in_full[hb]);
+        };
+        // fetch frame g (g >= 1: once the producers have taken frame g - 1 out of the buffers)
+        uint32_t fetched = 0;                                 // frames fetched so far
+        auto fetch_frame = [&](bool blocking) {
+            const uint32_t g = fetched;
+            if (g >= n_mine) return;
+            if (g > 0) {
+                if (blocking) mbar_wait(in_empty, (g - 1) & 1);
+                else if (!mbar_try_wait(in_empty, (g - 1) & 1)) return;
+            }
+            const uint8_t* nf = frame_of(g);
+            int fb;
+            if (in.step(nf, fb)) {
+                fetch_half(nf + N64K, fb);
             } else {
                 fetch_half(nf, 0);
                 fetch_half(nf + N64K, 1);
-                ++n_fetch0;
-                ++n_fetch1;
-                lo_buf = 0;
             }
-            held_hi = nf + N64K;
-        }
+            ++fetched;
+        };
+        fetch_frame(true);
+        fetch_frame(true);
 
-        // ---- phase 2: column 256 rank + tid ----
-        mbar_wait(z_full, it & 1);
-        c64 z[64];
+        const float dboff = p.db_offset - 16.0f * DB_PER_LOG2;
+        for (uint32_t it = 0; it < n_mine; ++it) {
+            const size_t row_base = (size_t) (item_begin + it) * N64K;
+            mbar_wait(z_full, it & 1);
+            if (ct == 0 && it + 1 < n_mine) mbar_arrive_expect_tx(z_full, C64_Z_BYTES);
+#pragma unroll 1
+            for (int jc = 0; jc < 2; ++jc) {
+                const int kl = 64 * cw + 32 * jc + lane;      // column within this CTA
+                c64 z[64];
 #pragma unroll
-        for (int r = 0; r < 64; ++r) z[bitrev<64>(r)] = Zl[r * 256 + tid];
-        if (tid == 0 && it + 1 < n_mine) mbar_arrive_expect_tx(z_full, C64_Z_BYTES);
-        __syncwarp();
-        if (lane == 0) {
+                for (int r = 0; r < 64; ++r) z[bitrev<64>(r)] = Zl[r * 256 + kl];
+                fft_dit64(z);
+                // This warp no longer needs its columns of run jc: tell the four CTAs' producers.  The hand-back only
+                // has to keep their next stores behind OUR LOADS (write after read), and loads are over once their
+                // values exist: every output of the transform depends on all 64 loaded values, and the barrier address
+                // below depends on an output (the comparison is never true: 0x7fc12345 is a NaN no sum produces), so
+                // the arrive cannot issue before the last load has returned -- without any fence.
+                {
+                    float x0r, x0i;
+                    cunpack(z[0], x0r, x0i);
+                    const uint32_t dep = __float_as_uint(x0r) == 0x7fc12345u ? 4u : 0u;
+                    const uint32_t all = __reduce_or_sync(0xffffffffu, dep);     // every lane's loads, not just lane 0's
+                    if (lane == 0) {
 #pragma unroll
-            for (int d = 0; d < CL; ++d) mbar_arrive_remote(zfree_dst[d]);
-        }
-        fft_dit64(z);
-        const int k = 256 * (int) rank + tid;
-#pragma unroll
-        for (int q = 0; q < 64; ++q) {
-            float re, im;
-            cunpack(z[q], re, im);
-            const float pw = fmaf(re, re, im * im);
-            const float db = fmaf(DB_PER_LOG2, lg2_ftz(pw), dboff);
-            // fftshift (spectrum.c:25); bin N-1 also supplies the DC position (spectrum.c:30-33 with K = 1)
-            const bool last = (k == 1023 && q == 63);
-            const bool first = (k == 0 && q == 0);
-            const size_t at = row_base + (size_t) (1024 * ((q + 32) & 63) + k);
-            if (!first) {
-                if (p.db) __stcs(p.db + at, db);
-                if (p.power) __stcs(p.power + at, pw * FFT1024_POWER_SCALE);
-                if (p.db_u8) {
-                    int m = __float2int_rz(db);
-                    m = m < 0 ? 0 : (m > 255 ? 255 : m);
-                    p.db_u8[at] = (uint8_t) m;
+                        for (int d = 0; d < CL; ++d) mbar_arrive_remote_relaxed((zfree_dst[d] + 8 * jc) ^ all);
+                    }
                 }
-            }
-            if (last) {
-                const size_t dc = row_base + N64K / 2;
-                if (p.db) __stcs(p.db + dc, db);
-                if (p.power) __stcs(p.power + dc, pw * FFT1024_POWER_SCALE);
-                if (p.db_u8) {
-                    int m = __float2int_rz(db);
-                    m = m < 0 ? 0 : (m > 255 ? 255 : m);
-                    p.db_u8[dc] = (uint8_t) m;
+                const int k = 256 * (int) rank + kl;
+#pragma unroll
+                for (int q = 0; q < 64; ++q) {
+                    float re, im;
+                    cunpack(z[q], re, im);
+                    const float pw = fmaf(re, re, im * im);
+                    const float db = fmaf(DB_PER_LOG2, lg2_ftz(pw), dboff);
+                    // fftshift (spectrum.c:25); bin N-1 also supplies the DC position (spectrum.c:30-33 with K = 1)
+                    const bool last = (k == 1023 && q == 63);
+                    const bool first = (k == 0 && q == 0);
+                    const size_t at = row_base + (size_t) (1024 * ((q + 32) & 63) + k);
+                    if (!first) {
+                        if (p.db) __stcs(p.db + at, db);
+                        if (p.power) __stcs(p.power + at, pw * FFT1024_POWER_SCALE);
+                        if (p.db_u8) {
+                            int m = __float2int_rz(db);
+                            m = m < 0 ? 0 : (m > 255 ? 255 : m);
+                            p.db_u8[at] = (uint8_t) m;
+                        }
+                    }
+                    if (last) {
+                        const size_t dc = row_base + N64K / 2;
+                        if (p.db) __stcs(p.db + dc, db);
+                        if (p.power) __stcs(p.power + dc, pw * FFT1024_POWER_SCALE);
+                        if (p.db_u8) {
+                            int m = __float2int_rz(db);
+                            m = m < 0 ? 0 : (m > 255 ? 255 : m);
+                            p.db_u8[dc] = (uint8_t) m;
+                        }
+                    }
                 }
+                // the input of frame it + 2: as soon as the producers have emptied the buffers, at the latest now
+                if (fetched == it + 2) fetch_frame(jc == 1);
             }
         }
     }

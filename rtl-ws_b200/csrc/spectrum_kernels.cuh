@@ -28,6 +28,7 @@ struct Spec64kExtra {
     float2* scratch;              // [scratch_ctas][64][1024] complex: Z[r][k], L2-resident
     float* acc;                   // [scratch_ctas][65536] power accumulators (K > 1), else null
     const float2* twiddle_rk;     // [64][1024]: exp(-2*pi*i*r*k/65536)
+    const float2* twiddle_32x32;  // [32][32]: exp(-2*pi*i*n2*k1/1024), the inter-pass table of the 1024-point transform
     int scratch_ctas;
 };
 
