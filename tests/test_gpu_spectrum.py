@@ -339,9 +339,8 @@ def test_spectrogram_full_size_shift_property(pkg, cuda):
 def test_65536_cluster_kernel_equals_scratch_kernel(pkg, cuda, hop, window, n_streams, n_rows):
     """The opt-in four-CTA cluster kernel (Z in distributed shared memory, K = 1 rows) against the scratch kernel, whatever the
     hop, the window and the split of rows over clusters (more rows than clusters, rows that do not divide, a single
-    row).  Rectangular frames run the same instructions in the same order: bit-identical.  With the Hann window the
-    two kernels inline sincospif() in different contexts and the compiler contracts its polynomial differently, so
-    window values differ in the last bit: powers agree to 2e-5 of (bin + row mean), dB to 1e-3 above -30 dB."""
+    row).  The two kernels factor the last radix-2 stage differently (and inline sincospif() in different contexts),
+    so results differ by f32 rounding only: powers agree to 2e-5 of (bin + row mean), dB to 1e-3 above -30 dB."""
     torch = cuda
     n = 65536 + hop * (n_rows - 1)
     g = torch.Generator(device="cuda").manual_seed(hop + n_rows)
@@ -360,10 +359,6 @@ def test_65536_cluster_kernel_equals_scratch_kernel(pkg, cuda, hop, window, n_st
     assert pkg.launch_count() == before + 1
     for k in ("db", "power", "db_u8"):
         assert got[k].shape == (n_streams, n_rows, 65536)
-    if not window:
-        for k in ("db", "power", "db_u8"):
-            assert torch.equal(got[k], want[k]), k
-        return
     mean = want["power"].mean(dim=-1, keepdim=True)
     assert ((got["power"] - want["power"]).abs() <= 2e-5 * (want["power"] + mean)).all()
     loud = want["power"] > 1e-3 * mean
