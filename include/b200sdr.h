@@ -294,8 +294,10 @@ int b200_wire_spectrum_messages(const uint8_t* d_payload, int64_t payload_stride
  * first_wire_sample + 4096 m .. + 4095 of d_audio + s * audio_stride (floats), at
  * d_msgs + s * msg_stride + m * B200_WIRE_AUDIO_MESSAGE_BYTES.  flags = 0: wire sample w is audio
  * sample w.  B200_WIRE_REFERENCE_DRAIN: wire sample w is audio sample
- * b200_wire_reference_drain_index(w, buffer_len) (buffer_len = 5120, audio_main.c:90,100).
- * d_audio must start at the stream's first audio sample in that mode. */
+ * b200_wire_reference_drain_index(w, buffer_len) (buffer_len = 5120, audio_main.c:90,100; any multiple of 512 --
+ * other pool-buffer lengths make the reference copy partial chunks, which is refused rather than approximated).
+ * d_audio must start at the stream's first audio sample in that mode.  first_wire_sample + 4096 n_messages may
+ * not exceed audio_stride (the floats a row holds). */
 int b200_wire_audio_messages(const float* d_audio, int64_t audio_stride, int n_streams, int64_t first_wire_sample,
                              int n_messages, int flags, int buffer_len, uint8_t* d_msgs, int64_t msg_stride,
                              void* cuda_stream);

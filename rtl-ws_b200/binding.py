@@ -583,10 +583,18 @@ class PushStream:
         def on_payload(user, stream, first, k, ptr):
             self.payloads[stream].append((first, k, np.ctypeslib.as_array(ptr, shape=(1024,)).copy()))
 
-        self._cb = (SPECTRUM_SINK(on_spectrum) if self._frames else SPECTRUM_SINK(), AUDIO_SINK(on_audio), PAYLOAD_SINK(on_payload))
+        self._on_spectrum = SPECTRUM_SINK(on_spectrum)
+        self._cb = (self._on_spectrum if self._frames else SPECTRUM_SINK(), AUDIO_SINK(on_audio), PAYLOAD_SINK(on_payload))
         lib().b200_stream_set_sinks(self.h, self._cb[0], self._cb[1], None)
         if self._payload_K > 0:
             _check(lib().b200_stream_set_payload_sink(self.h, self._payload_K, self._cb[2]), "b200_stream_set_payload_sink")
+
+    def enable_frames(self) -> None:
+        """Install the per-frame dB sink on a stream that was created without one (frames=False): the library
+        allocates the row buffers now; batches submitted before this call deliver no rows."""
+        self._frames = True
+        self._cb = (self._on_spectrum, self._cb[1], self._cb[2])
+        lib().b200_stream_set_sinks(self.h, self._cb[0], self._cb[1], None)
 
     def push(self, stream: int, samples: np.ndarray) -> None:
         samples = np.ascontiguousarray(samples, dtype=np.uint8)

@@ -63,6 +63,7 @@ struct b200_stream {
         cudaEvent_t done[ST_SLOTS];
         bool in_flight[ST_SLOTS];
         bool ready[ST_SLOTS];      // full, not yet submitted
+        bool has_db[ST_SLOTS];     // the submitted slot computed and copied per-frame dB rows
     };
     std::vector<PerStream> st;
     b200_spectrum_sink spectrum_sink;
@@ -85,7 +86,8 @@ static void stream_deliver(b200_stream* s, int i, bool block)
         const size_t off = ((size_t) i * ST_SLOTS + slot);
         if (s->payload_sink && s->payload_K > 0)
             s->payload_sink(s->user, i, b * (s->batch / 1024), s->payload_K, s->h_payload + off * 1024);
-        if (s->spectrum_sink)
+        // a sink installed after this batch was submitted without one gets nothing for it (there are no rows)
+        if (s->spectrum_sink && p.has_db[slot])
             s->spectrum_sink(s->user, i, b * (s->batch / 1024), (int) (s->batch / 1024), s->h_db + off * (size_t) s->batch);
         if (s->audio_sink)
             s->audio_sink(s->user, i, b * (s->batch / (4 * s->R)), (int) (s->batch / (4 * s->R)), s->h_audio + off * (size_t) (s->batch / (4 * s->R)));
@@ -104,20 +106,22 @@ static int stream_submit_run(b200_stream* s, int a, int b, int slot)
     cudaStream_t lane = s->lanes[(a / ST_GROUP) % ST_LANES];
     const size_t off = (size_t) a * ST_SLOTS + (size_t) slot;            // first stream's slot; next stream: + ST_SLOTS
     uint8_t* d_batch = s->d_rows + (size_t) a * (size_t) s->row_bytes + 2 * (size_t) s->hist;
-    float* d_db = s->d_db + (size_t) a * batch;
+    // per-frame dB rows exist only once a spectrum sink has been installed (b200_stream_set_sinks allocates them)
+    const bool want_db = s->spectrum_sink != nullptr && s->d_db != nullptr && s->h_db != nullptr;
+    float* d_db = want_db ? s->d_db + (size_t) a * batch : nullptr;
     float* d_audio = s->d_audio + (size_t) a * n_audio;
     uint8_t* d_pay = s->d_payload + (size_t) a * 1024;
     const bool want_payload = s->payload_sink != nullptr && s->payload_K > 0;
     B200_CUDA_TRY(cudaMemcpy2DAsync(d_batch, (size_t) s->row_bytes, s->h_in + off * 2 * batch, ST_SLOTS * 2 * batch, 2 * batch,
                                     (size_t) n, cudaMemcpyHostToDevice, lane));
     // without a per-frame sink the dB rows are not computed at all: the FM kernel and the K-frame average only
-    int rc = b200_chain_exec_r(d_batch, s->row_bytes, n, s->batch, s->R, s->gain_db, s->spectrum_sink ? d_db : nullptr, d_audio,
+    int rc = b200_chain_exec_r(d_batch, s->row_bytes, n, s->batch, s->R, s->gain_db, d_db, d_audio,
                                (int64_t) n_audio, want_payload ? d_pay : nullptr, want_payload ? s->payload_K : 0, lane);
     if (rc) return rc;
     rc = launch_fm_history_carry(d_batch, s->row_bytes, n, s->batch, s->R, lane);
     if (rc) return rc;
     // the per-frame dB rows cross PCIe only if somebody listens (4 bytes per sample; the payload is 1 KB per batch)
-    if (s->spectrum_sink)
+    if (want_db)
         B200_CUDA_TRY(cudaMemcpy2DAsync(s->h_db + off * batch, ST_SLOTS * batch * sizeof(float), d_db, batch * sizeof(float),
                                         batch * sizeof(float), (size_t) n, cudaMemcpyDeviceToHost, lane));
     B200_CUDA_TRY(cudaMemcpy2DAsync(s->h_audio + off * n_audio, ST_SLOTS * n_audio * sizeof(float), d_audio,
@@ -130,6 +134,7 @@ static int stream_submit_run(b200_stream* s, int a, int b, int slot)
         B200_CUDA_TRY(cudaEventRecord(p.done[slot], lane));
         p.ready[slot] = false;
         p.in_flight[slot] = true;
+        p.has_db[slot] = want_db;
         ++p.batches_submitted;
     }
     return B200_OK;
@@ -219,10 +224,8 @@ b200_stream* b200_stream_create_r(int n_streams, int64_t batch_samples, int gain
     for (int i = 0; i < ST_LANES; ++i) s->lanes[i] = nullptr;
     const size_t ns = (size_t) n_streams;
     bool ok = cudaMalloc(&s->d_rows, ns * (size_t) s->row_bytes) == cudaSuccess;
-    ok = ok && cudaMalloc(&s->d_db, sizeof(float) * ns * (size_t) batch_samples) == cudaSuccess;
     ok = ok && cudaMalloc(&s->d_audio, sizeof(float) * ns * (size_t) (batch_samples / (4 * R))) == cudaSuccess;
     ok = ok && cudaHostAlloc(&s->h_in, ns * ST_SLOTS * 2 * (size_t) batch_samples, cudaHostAllocDefault) == cudaSuccess;
-    ok = ok && cudaHostAlloc(&s->h_db, sizeof(float) * ns * ST_SLOTS * (size_t) batch_samples, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&s->h_audio, sizeof(float) * ns * ST_SLOTS * (size_t) (batch_samples / (4 * R)), cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaMalloc(&s->d_payload, ns * 1024) == cudaSuccess;
     ok = ok && cudaHostAlloc(&s->h_payload, ns * ST_SLOTS * 1024, cudaHostAllocDefault) == cudaSuccess;
@@ -237,6 +240,7 @@ b200_stream* b200_stream_create_r(int n_streams, int64_t batch_samples, int gain
             s->st[i].done[k] = nullptr;
             s->st[i].in_flight[k] = false;
             s->st[i].ready[k] = false;
+            s->st[i].has_db[k] = false;
             if (ok) ok = cudaEventCreateWithFlags(&s->st[i].done[k], cudaEventDisableTiming) == cudaSuccess;
         }
     }
@@ -275,6 +279,21 @@ void b200_stream_destroy(b200_stream* s)
 
 void b200_stream_set_sinks(b200_stream* s, b200_spectrum_sink spectrum_sink, b200_audio_sink audio_sink, void* user)
 {
+    if (s == nullptr) return;
+    // The per-frame dB rows (4 bytes per sample on the device, twice that pinned on the host: 420 MB for 256 streams
+    // of 204800 samples) exist only for callers that listen to them: allocated when the first spectrum sink arrives.
+    if (spectrum_sink != nullptr && s->d_db == nullptr) {
+        const size_t ns = (size_t) s->n_streams;
+        bool ok = cudaMalloc(&s->d_db, sizeof(float) * ns * (size_t) s->batch) == cudaSuccess;
+        ok = ok && cudaHostAlloc(&s->h_db, sizeof(float) * ns * ST_SLOTS * (size_t) s->batch, cudaHostAllocDefault) == cudaSuccess;
+        if (!ok) {
+            set_error("stream: dB row buffers: %s", cudaGetErrorString(cudaGetLastError()));
+            if (s->d_db) cudaFree(s->d_db);
+            s->d_db = nullptr;
+            s->h_db = nullptr;
+            spectrum_sink = nullptr;      // reported through b200_last_error(); audio and payload keep working
+        }
+    }
     s->spectrum_sink = spectrum_sink;
     s->audio_sink = audio_sink;
     s->user = user;

@@ -256,6 +256,21 @@ int b200_wire_audio_messages(const float* d_audio, int64_t audio_stride, int n_s
         set_error("b200_wire_audio_messages: audio / message pointers and strides must be multiples of 8 bytes");
         return B200_ERR_ALIGN;
     }
+    // drain_index() models the reference's cursor for pool buffers that a whole number of 512-sample calls fills
+    // (5120 at R = 10, rf_decimator.c:65-66 / audio_main.c:90); at other lengths the call that reaches the buffer end
+    // copies a partial chunk, which is not modelled -- refuse instead of emitting a stream that differs from the reference
+    if (drain && buffer_len % (B200_WIRE_AUDIO_FRAGMENT_BYTES / 4) != 0) {
+        set_error("b200_wire_audio_messages: B200_WIRE_REFERENCE_DRAIN needs buffer_len to be a multiple of %d (got %d)",
+                  B200_WIRE_AUDIO_FRAGMENT_BYTES / 4, buffer_len);
+        return B200_ERR_ARG;
+    }
+    // a row of d_audio holds at most audio_stride floats: the messages may not read past it
+    if (first_wire_sample + (int64_t) n_messages * AUDIO_FLOATS > audio_stride) {
+        set_error("b200_wire_audio_messages: wire samples %lld .. %lld lie outside an audio row of %lld floats",
+                  (long long) first_wire_sample, (long long) (first_wire_sample + (int64_t) n_messages * AUDIO_FLOATS),
+                  (long long) audio_stride);
+        return B200_ERR_ARG;
+    }
     if (msg_stride < (int64_t) n_messages * B200_WIRE_AUDIO_MESSAGE_BYTES) {
         set_error("b200_wire_audio_messages: msg_stride %lld < %lld", (long long) msg_stride,
                   (long long) n_messages * B200_WIRE_AUDIO_MESSAGE_BYTES);

@@ -261,6 +261,28 @@ def test_push_stream_payload_sink(pkg, cuda, po, synth):
     ps.close()
 
 
+def test_push_stream_spectrum_sink_installed_late(pkg, cuda, po, synth):
+    """The per-frame dB buffers are allocated when a spectrum sink first arrives.  A stream that ran payload-only and
+    gets its sink after two batches delivers rows for the later batches only -- never uninitialised memory for the
+    earlier ones -- and audio and payloads are unaffected."""
+    batch, n_batches = 204800, 4
+    iq = synth.s2_tones(batch * n_batches, seed=171)
+    ps = pkg.PushStream(1, batch, payload_K=6, frames=False)
+    ps.push(0, iq[:2 * batch])
+    ps.flush()
+    assert ps.spectra[0] == [] and len(ps.payloads[0]) == 2
+    ps.enable_frames()
+    ps.push(0, iq[2 * batch:])
+    ps.flush()
+    assert [f for f, _ in ps.spectra[0]] == [2 * (batch // 1024), 3 * (batch // 1024)]
+    assert len(ps.payloads[0]) == 4 and len(ps.audio[0]) == 4
+    db = np.concatenate([r for _, r in ps.spectra[0]])
+    rows = po.Spectrum(1024).rows(iq[2 * batch:])
+    ok = rows > 1e-6 * rows.mean(axis=1, keepdims=True)
+    assert np.abs(db[ok] - 10 * np.log10(rows[ok])).max() <= 0.01
+    ps.close()
+
+
 def test_push_stream_like_a_signal_source_callback(pkg, cuda, po, synth):
     """Three dongles pushing 131072-sample source buffers (signal_source.c:31) in round robin;
     batches of one reference block (204800 samples); sinks receive everything in order."""

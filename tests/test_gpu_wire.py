@@ -72,6 +72,21 @@ def test_audio_messages_equal_numpy(pkg, cuda, wire, flags):
         assert (src != w).sum() == 512 * ((first + n_msgs * 4096 - 1) // 5120 - (first - 1) // 5120)
 
 
+def test_audio_messages_argument_errors(pkg, cuda, wire):
+    """Drain mode models the reference's cursor only for pool buffers that whole 512-sample calls fill (5120 at
+    R = 10; 6400 at R = 8 is refused, not approximated), and messages may not read past an audio row."""
+    torch = cuda
+    d_audio = torch.zeros((2, 3 * 4096), dtype=torch.float32, device="cuda")
+    wire.audio_messages(d_audio, 0, 3, flags=wire.REFERENCE_DRAIN, buffer_len=5120)
+    wire.audio_messages(d_audio, 0, 3, flags=0, buffer_len=6400)              # buffer_len is unused without the flag
+    with pytest.raises(pkg.B200Error):
+        wire.audio_messages(d_audio, 0, 3, flags=wire.REFERENCE_DRAIN, buffer_len=6400)
+    with pytest.raises(pkg.B200Error):
+        wire.audio_messages(d_audio, 0, 4)                                    # 4 x 4096 > the 12288 floats of a row
+    with pytest.raises(pkg.B200Error):
+        wire.audio_messages(d_audio, 4096, 3)
+
+
 def test_product_path_against_golden_ws_stream(pkg, cuda, po, synth, wire):
     """IQ -> GPU kernels -> GPU wire emitters, compared with what main.c put on the socket."""
     torch = cuda
