@@ -84,7 +84,7 @@ int spectrum_generic_scratch_ctas();
 int launch_spectrum4096(const SpecParams& p, cudaStream_t stream);
 int launch_spectrum2048(const SpecParams& p, cudaStream_t stream);
 int launch_spectrum_mx1024(const SpecParams& p, int N, cudaStream_t stream);
-int launch_spectrum64k(const SpecParams& p, const Spec64kExtra& x, cudaStream_t stream);
+int launch_spectrum64k(const SpecParams& p, const Spec64kExtra& x, int N, cudaStream_t stream);
 int launch_spectrum64k_cluster(const SpecParams& p, const Spec64kExtra& x, cudaStream_t stream);
 int launch_fm_chain(const FmParams& p, cudaStream_t stream);
 int launch_fm_history_carry(uint8_t* iq, int64_t stride, int n_streams, int64_t n_samples, int R, cudaStream_t stream);
@@ -232,7 +232,8 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
     pl->gen_acc = nullptr;
     pl->gen_ctas = 0;
     pl->d_twiddle = upload_twiddles(N);
-    const bool wants1024 = (N == 2048 || N == 4096 || N == 8192 || N == 65536);
+    const bool four_step = (N == 16384 || N == 32768 || N == 65536);      // spectrum64k.cu, R = N / 1024 branches
+    const bool wants1024 = (N == 2048 || N == 4096 || N == 8192 || four_step);
     if (pl->d_twiddle != nullptr && wants1024) pl->d_twiddle1024 = upload_twiddles(1024);
     if (pl->d_twiddle == nullptr || (wants1024 && pl->d_twiddle1024 == nullptr)) {
         set_error("spectrum plan: twiddle upload failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -284,12 +285,13 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
             return nullptr;
         }
     }
-    if (N == 65536) {
+    if (four_step) {
         // tables in the layout the four-step kernel reads coalesced, and its L2-resident scratch
-        std::vector<float2> trk((size_t) 64 * 1024);
-        for (int r = 0; r < 64; ++r)
+        const int Rb = N / 1024;
+        std::vector<float2> trk((size_t) Rb * 1024);
+        for (int r = 0; r < Rb; ++r)
             for (int k = 0; k < 1024; ++k) {
-                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double) ((long long) r * k) / 65536.0L;
+                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double) ((long long) r * k) / (long double) N;
                 trk[(size_t) r * 1024 + k] = make_float2((float) cosl(a), (float) sinl(a));
             }
         bool ok = cudaMalloc((void**) &pl->x64.twiddle_rk, sizeof(float2) * trk.size()) == cudaSuccess &&
@@ -303,10 +305,10 @@ b200_spectrum_plan* b200_spectrum_plan_create(int N, int hop, int K, int64_t row
         ok = ok && cudaMalloc((void**) &pl->x64.twiddle_32x32, sizeof(float2) * t32.size()) == cudaSuccess &&
              cudaMemcpy((void*) pl->x64.twiddle_32x32, t32.data(), sizeof(float2) * t32.size(), cudaMemcpyHostToDevice) == cudaSuccess;
         pl->x64.scratch_ctas = sm_count();
-        ok = ok && cudaMalloc((void**) &pl->x64.scratch, sizeof(float2) * 65536 * (size_t) pl->x64.scratch_ctas) == cudaSuccess;
-        if (ok && K > 1) ok = cudaMalloc((void**) &pl->x64.acc, sizeof(float) * 65536 * (size_t) pl->x64.scratch_ctas) == cudaSuccess;
+        ok = ok && cudaMalloc((void**) &pl->x64.scratch, sizeof(float2) * (size_t) N * (size_t) pl->x64.scratch_ctas) == cudaSuccess;
+        if (ok && K > 1) ok = cudaMalloc((void**) &pl->x64.acc, sizeof(float) * (size_t) N * (size_t) pl->x64.scratch_ctas) == cudaSuccess;
         if (!ok) {
-            set_error("spectrum plan: 65536-point tables / scratch: %s", cudaGetErrorString(cudaGetLastError()));
+            set_error("spectrum plan: four-step tables / scratch: %s", cudaGetErrorString(cudaGetLastError()));
             b200_spectrum_plan_destroy(pl);
             return nullptr;
         }
@@ -385,13 +387,15 @@ static int spectrum_exec_kind(b200_spectrum_plan* plan, const void* d_in, int64_
             return B200_ERR_ALIGN;
         }
         p.twiddle = plan->d_twiddle1024;
-        p.twiddle_n = plan->N == 65536 ? plan->d_twiddle : plan->d_twiddle_rk;
-        if (plan->N == 65536) {
+        const bool four_step = plan->x64.twiddle_rk != nullptr;
+        p.twiddle_n = four_step ? plan->d_twiddle : plan->d_twiddle_rk;
+        if (four_step) {
             // B200_S64K_CLUSTER=1 selects the four-CTA cluster kernel (Z in distributed shared memory, K = 1 rows;
             // spectrum64k_cluster.cu): DRAM traffic 1.0x algorithmic but 90 vs 125 Gsamples/s, so it is not the default.
             const char* env = getenv("B200_S64K_CLUSTER");
-            if (plan->K == 1 && env != nullptr && atoi(env) != 0) return launch_spectrum64k_cluster(p, plan->x64, stream);
-            return with_plan_scratch(plan, stream, [&] { return launch_spectrum64k(p, plan->x64, stream); });
+            if (plan->N == 65536 && plan->K == 1 && env != nullptr && atoi(env) != 0)
+                return launch_spectrum64k_cluster(p, plan->x64, stream);
+            return with_plan_scratch(plan, stream, [&] { return launch_spectrum64k(p, plan->x64, plan->N, stream); });
         }
         if (plan->N == 4096) {
             p.twiddle_n = plan->d_twiddle_4k;

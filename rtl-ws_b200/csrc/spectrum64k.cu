@@ -1,6 +1,8 @@
 // spectrum64k.cu -- 65536-point power spectra (BASELINE config 4: wideband spectrogram,
 // Hann window, 50 % overlap), one CTA per frame, four-step through an L2-resident scratch
-// (sm_100a).
+// (sm_100a).  The same kernel, with R = N / 1024 polyphase branches as a template parameter, serves N = 16384
+// (R = 16) and 32768 (R = 32), which no other kernel of the library covers (the generic kernel ran them below
+// 100 Gsamples/s).  The description below is for R = 64.
 //
 // 65536 = 64 x 1024, decimation in time by 64:
 //   X[k + 1024 q] = sum_{r<64} W_64^(r q) * ( W_N^(r k) * F_r[k] ),   F_r = FFT_1024( x[64 m + r] ).
@@ -26,20 +28,36 @@ namespace b200 {
 
 namespace {
 
-constexpr int N64K = 65536;
 constexpr int S64_THREADS = 256;
-constexpr int S64_WARPS = 8;                                              // 64 branches and 1024 columns divide evenly
-constexpr int S64_FRAME_BYTES = 2 * N64K;                                  // 131072
-constexpr int S64_SMEM = S64_FRAME_BYTES + S64_WARPS * FFT1024_XCH_BYTES + 16;
+constexpr int S64_WARPS = 8;                                              // R branches and 1024 columns divide evenly
+constexpr int s64_smem(int R) { return 2 * 1024 * R + S64_WARPS * FFT1024_XCH_BYTES + 16; }
 
-template <bool WINDOW, bool MULTI>
+// R-point in-register transform of phase 2 (input in bit-reversed order, output natural)
+template <int R>
+__device__ __forceinline__ void fft_columns(c64 (&z)[R])
+{
+    if constexpr (R == 64) {
+        fft_dit64(z);
+    } else if constexpr (R == 32) {
+        float2 unused[32];
+        fft_dit32<false>(z, unused);
+    } else {
+        fft_dit_small<R>(z);
+    }
+}
+
+template <int R, bool WINDOW, bool MULTI>
 __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecParams p, const Spec64kExtra x)
 {
+    constexpr int N64K = 1024 * R;                      // the frame length of this instantiation (65536 for R = 64)
+    constexpr int S64_FRAME_BYTES = 2 * N64K;
+    constexpr int WPR = R / 2;                          // 32-bit words per row (one m, all R branches)
+    constexpr int RP = 32 / WPR;                        // rows per 128 bytes
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    uint32_t* frame32 = reinterpret_cast<uint32_t*>(smem);                 // [1024 rows][32 words], swizzled
+    uint32_t* frame32 = reinterpret_cast<uint32_t*>(smem);                 // [1024 rows][WPR words], swizzled
     float2* xch = reinterpret_cast<float2*>(smem + S64_FRAME_BYTES + warp * FFT1024_XCH_BYTES);
     float* dc_slot = reinterpret_cast<float*>(smem + S64_FRAME_BYTES + S64_WARPS * FFT1024_XCH_BYTES);
 
@@ -80,18 +98,20 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
         const int64_t row = item - s * p.n_rows;
         return p.iq + s * p.stream_stride_bytes + 2 * (row * p.row_hop + (int64_t) j * p.hop);
     };
-    // 0. frame -> shared memory with 4-byte cp.async copies (LDGSTS: no registers, nothing waits), rows word-swizzled
-    //    by (m mod 32): word w of logical row m lands in word w ^ (m & 31) of physical row m ^ flip_.  Thread t
-    //    copies word (t & 31) of rows (t >> 5) + 8 i.  The fetch of frame seq + 1 is issued as soon as phase 1 of frame
-    //    seq is over (its bytes are dead then) and lands while phase 2 runs.
+    // 0. frame -> shared memory with 4-byte cp.async copies (LDGSTS: no registers, nothing waits).  A row (one m,
+    //    all R branches) is WPR words; word w of logical row m lands in word w ^ ((m / RP) % WPR) of physical row
+    //    m ^ flip_, so that the stride-(2R)-byte reads of a branch hit 32 different banks (RP rows share 128 bytes).
+    //    Thread t copies words t + 256 i.  The fetch of frame seq + 1 is issued as soon as phase 1 of frame seq is over
+    //    (its bytes are dead then) and lands while phase 2 runs.
     auto fetch = [&](const uint8_t* frame, int flip_, bool half) {
         const uint32_t dst0 = smem_u32(frame32);
         const uint8_t* src0 = frame + 4 * tid;
 #pragma unroll 8
-        for (int i = half ? 64 : 0; i < 128; ++i) {
-            const int m = warp + 8 * i;
-            const uint32_t dst = dst0 + (uint32_t) ((m ^ flip_) * 128 + 4 * (lane ^ (m & 31)));
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src0 + 1024 * i) : "memory");
+        for (int i = half ? R : 0; i < 2 * R; ++i) {
+            const int W = tid + S64_THREADS * i;
+            const int m = W / WPR, w = W % WPR;
+            const uint32_t dst = dst0 + (uint32_t) (((m ^ flip_) * WPR + (w ^ ((m / RP) % WPR))) * 4);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src0 + 4 * S64_THREADS * i) : "memory");
         }
     };
     if (n_seq > 0) fetch(frame_of(0), 0, false);
@@ -110,24 +130,25 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
             //         are re-read per frame so that they are not live during phase 2) ----
             float2 tw[32];
             fft1024_load_twiddles(p.twiddle, lane, tw);
-            for (int r = warp; r < 64; r += S64_WARPS) {
+            for (int r = warp; r < R; r += S64_WARPS) {
                 c64 a[32];
-                // Hann window of sample 64*(32*n1 + lane) + r without a table:
-                //   w = 1/2 - 1/2 cos(2 pi n1 / 32 + phi),  phi = 2 pi (64 lane + r) / 65536
+                // Hann window of sample R*(32*n1 + lane) + r without a table:
+                //   w = 1/2 - 1/2 cos(2 pi n1 / 32 + phi),  phi = 2 pi (R lane + r) / N
                 // (the [r][m] window table cost 256 KB of L2 reads per frame per SM)
                 float cphi = 1.0f, sphi = 0.0f;
-                if (WINDOW) sincospif((float) (64 * lane + r) * (1.0f / 32768.0f), &sphi, &cphi);
+                if (WINDOW) sincospif((float) (R * lane + r) * (2.0f / (float) N64K), &sphi, &cphi);
                 {
                     const c64 bias1 = cpack(8421376.0f, 8421376.0f);        // 2^23 + 256 * 128
                     // rows m < 512 (n1 < 16) and m >= 512 sit in the halves chosen by `flip`: two base pointers,
-                    // every load still base + compile-time offset
-                    const uint8_t* fb_lo = reinterpret_cast<const uint8_t*>(frame32) + flip * 128;
-                    const uint8_t* fb_hi = reinterpret_cast<const uint8_t*>(frame32) - flip * 128;
+                    // every load still base + compile-time offset; m = 32 n1 + lane, so the swizzle is per lane
+                    const int sw = (lane / RP) % WPR;
+                    const int col = (((r >> 1) ^ sw) << 2) + ((r & 1) << 1);
+                    const uint8_t* fb_lo = reinterpret_cast<const uint8_t*>(frame32) + flip * (2 * R) + lane * (2 * R) + col;
+                    const uint8_t* fb_hi = reinterpret_cast<const uint8_t*>(frame32) - flip * (2 * R) + lane * (2 * R) + col;
 #pragma unroll
                     for (int n1 = 0; n1 < 32; ++n1) {
-                        const int m = 32 * n1 + lane;                       // m mod 32 == lane
                         const uint8_t* fb = n1 < 16 ? fb_lo : fb_hi;
-                        const uint32_t v = *reinterpret_cast<const uint16_t*>(fb + m * 128 + (((r >> 1) ^ lane) << 2) + ((r & 1) << 1));
+                        const uint32_t v = *reinterpret_cast<const uint16_t*>(fb + 32 * n1 * (2 * R));
                         const int q = bitrev<32>(n1);
                         a[q] = cpack(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7504)),
                                      __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7514)));
@@ -161,16 +182,16 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
                 fetch(next, flip, half);
             }
 
-            // ---- 2. 64-point transforms across r for k = tid + 320 g ----
+            // ---- 2. R-point transforms across r for k = tid + 256 g ----
             for (int g = 0; g < (1024 + S64_THREADS - 1) / S64_THREADS; ++g) {
                 const int k = tid + S64_THREADS * g;
                 if (k >= 1024) break;
-                c64 z[64];
+                c64 z[R];
 #pragma unroll
-                for (int r = 0; r < 64; ++r) z[bitrev<64>(r)] = Z[r * 1024 + k];
-                fft_dit64(z);
+                for (int r = 0; r < R; ++r) z[bitrev<R>(r)] = Z[r * 1024 + k];
+                fft_columns<R>(z);
 #pragma unroll
-                for (int q = 0; q < 64; ++q) {
+                for (int q = 0; q < R; ++q) {
                     float re, im;
                     cunpack(z[q], re, im);
                     const float pw = fmaf(re, re, im * im);
@@ -180,7 +201,7 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
                     } else if (bin != 0) {
                         emit(row_base, bin, pw);
                     }
-                    if (k == 1023 && q == 63) dcacc = fmaf((float) (K - j), pw, dcacc);  // bin N-1
+                    if (k == 1023 && q == R - 1) dcacc = fmaf((float) (K - j), pw, dcacc);  // bin N-1
                 }
             }
             if (j == K - 1 && tid == 1023 % S64_THREADS) *dc_slot = dcacc;
@@ -204,24 +225,36 @@ __global__ void __launch_bounds__(S64_THREADS, 1) spectrum64k_kernel(const SpecP
     }
 }
 
-}  // namespace
-
 // Tried and dropped (round 2, measured): asking the L2 to keep the Z scratch -- an access-policy window with the
 // persisting property over the 74 MB, backed by a set-aside of the same size.  DRAM writes went UP (6.9 -> 11.9 GB per
 // 524 M samples: what is left of the L2 no longer absorbs the streaming rows) and the kernel lost 3 % (123 -> 119
 // Gsamples/s).  The four-CTA cluster kernel (spectrum64k_cluster.cu) removes the scratch altogether.
-int launch_spectrum64k(const SpecParams& p, const Spec64kExtra& x, cudaStream_t stream)
+template <int R>
+static int launch_scratch(const SpecParams& p, const Spec64kExtra& x, cudaStream_t stream)
 {
     const int64_t total = (int64_t) p.n_streams * p.n_rows;
     if (total == 0) return B200_OK;
-    auto kern = p.K > 1 ? (p.window ? spectrum64k_kernel<true, true> : spectrum64k_kernel<false, true>)
-                        : (p.window ? spectrum64k_kernel<true, false> : spectrum64k_kernel<false, false>);
-    if (int rc = ensure_dynamic_smem((const void*) kern, S64_SMEM)) return rc;
+    auto kern = p.K > 1 ? (p.window ? spectrum64k_kernel<R, true, true> : spectrum64k_kernel<R, false, true>)
+                        : (p.window ? spectrum64k_kernel<R, true, false> : spectrum64k_kernel<R, false, false>);
+    if (int rc = ensure_dynamic_smem((const void*) kern, s64_smem(R))) return rc;
     int64_t grid = x.scratch_ctas;
     if (grid > total) grid = total;
-    kern<<<(unsigned) grid, S64_THREADS, S64_SMEM, stream>>>(p, x);
+    kern<<<(unsigned) grid, S64_THREADS, s64_smem(R), stream>>>(p, x);
     B200_LAUNCH_CHECK();
     return B200_OK;
+}
+
+}  // namespace
+
+// N = 65536 (and, through the same kernel, 16384 and 32768): x.scratch holds [scratch_ctas][N] complex, x.twiddle_rk
+// [N / 1024][1024], x.acc [scratch_ctas][N] floats when K > 1
+int launch_spectrum64k(const SpecParams& p, const Spec64kExtra& x, int N, cudaStream_t stream)
+{
+    if (N == 65536) return launch_scratch<64>(p, x, stream);
+    if (N == 32768) return launch_scratch<32>(p, x, stream);
+    if (N == 16384) return launch_scratch<16>(p, x, stream);
+    set_error("spectrum: the four-step kernel covers N = 16384, 32768, 65536 (got %d)", N);
+    return B200_ERR_ARG;
 }
 
 }  // namespace b200

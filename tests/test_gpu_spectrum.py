@@ -143,7 +143,8 @@ def test_strided_stream_rows_and_empty(pkg, cuda, po, synth):
         pkg.SpectrumPlan(1024, hop=100)
 
 
-@pytest.mark.parametrize("N,K", [(16, 1), (256, 2), (2048, 1), (4096, 1), (4096, 3), (8192, 1), (16384, 1), (65536, 1)])
+@pytest.mark.parametrize("N,K", [(16, 1), (256, 2), (2048, 1), (4096, 1), (4096, 3), (8192, 1), (16384, 1), (16384, 3), (32768, 1),
+                                 (32768, 2), (65536, 1)])
 def test_other_frame_lengths(pkg, cuda, po, synth, N, K):
     iq = synth.s2_tones(N * K * 2 + 8, N=N, seed=N % 97)
     out = run_plan(pkg, cuda, iq, N=N, K=K)
@@ -169,6 +170,36 @@ def test_persistent_loop_many_rows(pkg, cuda, po, synth, N, rows):
     want = po.Spectrum(N, window=synth.hann(N)).rows(iq[:N * 200], hop=N // 2, K=2)
     check_power(out["power"][0], want)
     check_db(out["db"][0], want, K=2)
+
+
+@pytest.mark.parametrize("N,rows", [(16384, 400), (32768, 210)])
+def test_four_step_kernel_16384_32768(pkg, cuda, po, synth, N, rows):
+    """N = 16384 and 32768 run the 65536-point kernel's four-step form with 16 / 32 polyphase branches: more rows than
+    CTAs (each CTA walks a run of frames), rectangular with hop = N, Hann at 50 % overlap (half-frame re-use and the
+    row swizzle of the narrower rows), K = 2 accumulation, two streams, u8 payload bytes.  dB tolerance as for the
+    65536-point frames: millions of bins through 14-15 f32 stages hold 0.01 dB above -40 dB of
+    the frame mean and 0.03 dB between -60 and -40 dB."""
+    def check_db_long(got, want, K=1):
+        check_db(got, want, K=K, floor=1e-4)
+        check_db(got, want, K=K, floor=1e-6, tol=0.03)
+
+    iq = np.stack([synth.s2_tones(N * rows // 2, N=N, seed=N % 83 + s) for s in range(2)])
+    out = run_plan(pkg, cuda, iq, N=N)
+    for s in range(2):
+        want = po.Spectrum(N).rows(iq[s])
+        assert out["power"].shape == (2, rows // 2, N)
+        check_power(out["power"][s], want)
+        check_db_long(out["db"][s], want)
+        check_payload(out["db_u8"][s][::37], want[::37], 1, 0, po)
+    out = run_plan(pkg, cuda, iq, N=N, hop=N // 2, window=pkg.WINDOW_HANN)
+    for s in range(2):
+        want = po.Spectrum(N, window=synth.hann(N)).rows(iq[s], hop=N // 2)
+        check_power(out["power"][s], want)
+        check_db_long(out["db"][s], want)
+    out = run_plan(pkg, cuda, iq[0], N=N, K=2, hop=N // 2, window=pkg.WINDOW_HANN)
+    want = po.Spectrum(N, window=synth.hann(N)).rows(iq[0], hop=N // 2, K=2)
+    check_power(out["power"][0], want)
+    check_db_long(out["db"][0], want, K=2)
 
 
 def test_goldens_n4096_n65536(pkg, cuda, synth):

@@ -42,6 +42,10 @@ plan1k_h = pkg.SpectrumPlan(1024, window=pkg.WINDOW_HANN)
 plan4k_h = pkg.SpectrumPlan(4096, window=pkg.WINDOW_HANN)
 plan8k = pkg.SpectrumPlan(8192)
 db8k = torch.empty((S, L // 8192, 8192), dtype=torch.float32, device="cuda")
+plan16k = pkg.SpectrumPlan(16384)
+db16k = torch.empty((S, L // 16384, 16384), dtype=torch.float32, device="cuda")
+plan32k = pkg.SpectrumPlan(32768)
+db32k = torch.empty((S, L // 32768, 32768), dtype=torch.float32, device="cuda")
 plan2k = pkg.SpectrumPlan(2048)
 db2k = torch.empty((S, L // 2048, 2048), dtype=torch.float32, device="cuda")
 
@@ -55,6 +59,8 @@ cases = {
     "spectrum4096_hann_db": (lambda: plan4k_h.exec(ring.batch, db=True, out={"db": db4k}), 6.0),
     "spectrum2048_db": (lambda: plan2k.exec(ring.batch, db=True, out={"db": db2k}), 6.0),
     "spectrum8192_db": (lambda: plan8k.exec(ring.batch, db=True, out={"db": db8k}), 6.0),
+    "spectrum16384_db": (lambda: plan16k.exec(ring.batch, db=True, out={"db": db16k}), 6.0),
+    "spectrum32768_db": (lambda: plan32k.exec(ring.batch, db=True, out={"db": db32k}), 6.0),
     "spectrum65536_hann_50pct": (lambda: plan64k.exec(ring.batch, db=True, out={"db": db64k}), 10.0),
 }
 for name, (fn, bps) in cases.items():
