@@ -24,6 +24,19 @@ big = pkg.StreamRing(1, 65536 * 2)
 big.load(pkg.synth.s2_tones(65536 * 2, N=65536)[None])
 pkg.SpectrumPlan(65536, hop=32768, window=1).exec(big.batch, db=True)
 pkg.SpectrumPlan(65536, K=2).exec(big.batch, power=True)
+# round 2: the four-step kernel at 16 / 32 branches, the opt-in cluster kernel, the cs32 demodulator, the audio extensions
+pkg.SpectrumPlan(16384, hop=8192, window=1).exec(big.batch, db=True, power=True, db_u8=True)
+pkg.SpectrumPlan(32768, K=2).exec(big.batch, db=True)
+os.environ["B200_S64K_CLUSTER"] = "1"
+pkg.SpectrumPlan(65536, hop=32768, window=1).exec(big.batch, db=True, power=True, db_u8=True)
+pkg.SpectrumPlan(65536).exec(big.batch, db=True)
+del os.environ["B200_S64K_CLUSTER"]
+dm = pkg.FmDemod()
+dm.block(dec[0][:4096].cpu().numpy(), want_demod=True)
+dm.block(dec[0][4096:8192].cpu().numpy(), want_audio=False)
+dm.close()
+st = torch.zeros((3, pkg.AUDIO_POST_STATE_FLOATS), dtype=torch.float32, device="cuda")
+pkg.audio_post(audio[:, :368], st, pkg.AUDIO_DEEMPH_50US | pkg.AUDIO_RESAMPLE_48K)
 r7 = pkg.StreamRing(2, 4 * 7 * 8 * 9, R=7)
 r7.load(np.stack([pkg.synth.s1_noise(4 * 7 * 8 * 9, seed=s) for s in range(2)]))
 pkg.fm_exec(r7, decimated=True)
