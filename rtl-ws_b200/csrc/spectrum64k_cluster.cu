@@ -19,6 +19,9 @@
 // The next frame's input is fetched while phase 2 runs; with 50 % overlap only the new half is fetched (the two
 // 16 KB half buffers alternate roles).  Arithmetic per frame is that of spectrum64k.cu instruction for
 // instruction (spectrum.c:15-58, cbb_main.c:112-128), so the two kernels agree bit for bit.
+#include <type_traits>
+#include <utility>
+
 #include "b200_common.cuh"
 #include "fft1024_warp.cuh"
 #include "spectrum_kernels.cuh"
@@ -70,11 +73,24 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32
     return r;
 }
 // 8-byte store into a (possibly remote) CTA's shared memory; the destination's mbarrier counts its bytes
+// (OFF is a compile-time byte offset folded into the instruction: no address arithmetic per store)
+template <int OFF>
 __device__ __forceinline__ void st_async_b64(uint32_t dst_cluster_addr, c64 v, uint32_t bar_cluster_addr)
 {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst_cluster_addr),
-                 "l"(v), "r"(bar_cluster_addr)
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0+%3], %1, [%2];" ::"r"(dst_cluster_addr),
+                 "l"(v), "r"(bar_cluster_addr), "n"(OFF)
                  : "memory");
+}
+// f(integral_constant<int, 0>) ... f(integral_constant<int, N - 1>): a loop whose index is a constant expression
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>)
+{
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+    static_for_impl(f, std::make_integer_sequence<int, N>{});
 }
 // Arrive on a (possibly remote) CTA's mbarrier WITHOUT release semantics: a release at cluster scope is a
 // MEMBAR.ALL.GPU in SASS, which waits for every global store the warp has in flight (64 spectrum stores per run:
@@ -185,6 +201,14 @@ __global__ void __launch_bounds__(C64_THREADS, 1) spectrum64k_cluster_kernel(con
             zfull_dst[d] = map_to_rank(smem_u32(z_full), d);
         }
         const int sw_in = (lane >> 2) & 7;
+        // the eight XOR patterns of the tile swizzle as pointers, so that every tile access is base + immediate
+        uint8_t* xw[8];
+        const uint8_t* xr[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            xw[j] = xch + ((((lane >> 1) ^ j) << 4) | ((lane & 1) << 3));
+            xr[j] = xch + 256 * lane + ((j ^ (lane & 7)) << 4);
+        }
         const float2* tw_lane = x.twiddle_32x32 + lane;       // [n2][k1] W_1024^(n2 k1), this lane's column (L1-resident)
 
         for (uint32_t it = 0; it < n_mine; ++it) {
@@ -231,15 +255,13 @@ __global__ void __launch_bounds__(C64_THREADS, 1) spectrum64k_cluster_kernel(con
                 for (int k1 = 0; k1 < 32; ++k1) {
                     float re, im;
                     cunpack(a[k1], re, im);
-                    *reinterpret_cast<float2*>(xch + 256 * k1 + ((((lane >> 1) ^ (k1 & 7)) << 4) | ((lane & 1) << 3))) =
-                        make_float2(re, im);
+                    *reinterpret_cast<float2*>(xw[k1 & 7] + 256 * k1) = make_float2(re, im);
                 }
                 __syncwarp();
                 c64 b[32];
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {
-                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xch + 256 * lane + 128 * (m >> 3) +
-                                                                               (((m & 7) ^ (lane & 7)) << 4));
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xr[m & 7] + 128 * (m >> 3));
                     b[bitrev<32>(2 * m)] = v.x;
                     b[bitrev<32>(2 * m + 1)] = v.y;
                 }
@@ -247,6 +269,8 @@ __global__ void __launch_bounds__(C64_THREADS, 1) spectrum64k_cluster_kernel(con
                 // W_N^(r k) F_r[k]: the table loads of half a row are issued together, ahead of their products (the
                 // st.async below are volatile: inside the push loop every load would be waited for on its own --
                 // measured, 56 % of all stall samples).  ld.global.cg: 128 KB per frame must not sweep the small L1.
+                // (Moving this product to the consumers, fused into their first butterfly stage, was measured: 94 vs
+                // 111 Gsamples/s -- 64 just-in-time L2 loads per column are worse than 32 batched ones per branch.)
                 const float2* twr = x.twiddle_rk + r * 1024 + lane;
                 if (r > 0) {
 #pragma unroll
@@ -266,22 +290,29 @@ __global__ void __launch_bounds__(C64_THREADS, 1) spectrum64k_cluster_kernel(con
                 // before the wait has succeeded), so the waits need no cluster-scope acquire -- which ptxas implements
                 // as CCTL.IVALL after every poll: measured, 27 % of all stall samples and an L1 that never keeps the
                 // twiddle table.
-                auto push = [&](int rr, int k2, c64 v) {
-                    const int d = k2 >> 3;
-                    st_async_b64(z_dst[d] + (uint32_t) ((rr * 256 + (k2 & 7) * 32) * 8), v, zfull_dst[d]);
-                };
+                // destination of element k2 of branch rr: CTA k2 >> 3, Z[rr][(k2 & 7) * 32 + lane]; per branch one base per
+                // destination, the rest is an immediate
+                uint32_t zrow[CL];
+#pragma unroll
+                for (int d = 0; d < CL; ++d) zrow[d] = z_dst[d] + (uint32_t) (r * 2048);
                 if (jb == 0) {
                     if (it > 0) mbar_wait(&z_free[0], (it - 1) & 1);
-#pragma unroll
-                    for (int k2 = 0; k2 < 32; k2 += 2) push(r, k2, b[k2]);
+                    static_for<16>([&](auto i) {
+                        constexpr int k2 = 2 * decltype(i)::value;
+                        st_async_b64<(k2 & 7) * 256>(zrow[k2 >> 3], b[k2], zfull_dst[k2 >> 3]);
+                    });
 #pragma unroll
                     for (int k2 = 1; k2 < 32; k2 += 2) held[k2 >> 1] = b[k2];
                 } else {
                     if (it > 0) mbar_wait(&z_free[1], (it - 1) & 1);
-#pragma unroll
-                    for (int k2 = 1; k2 < 32; k2 += 2) push(r - 1, k2, held[k2 >> 1]);
-#pragma unroll
-                    for (int k2 = 0; k2 < 32; ++k2) push(r, k2, b[k2]);
+                    static_for<16>([&](auto i) {
+                        constexpr int k2 = 2 * decltype(i)::value + 1;
+                        st_async_b64<(k2 & 7) * 256 - 2048>(zrow[k2 >> 3], held[k2 >> 1], zfull_dst[k2 >> 3]);     // branch r - 1
+                    });
+                    static_for<32>([&](auto i) {
+                        constexpr int k2 = decltype(i)::value;
+                        st_async_b64<(k2 & 7) * 256>(zrow[k2 >> 3], b[k2], zfull_dst[k2 >> 3]);
+                    });
                 }
             }
         }
@@ -327,6 +358,9 @@ __global__ void __launch_bounds__(C64_THREADS, 1) spectrum64k_cluster_kernel(con
         fetch_frame(true);
 
         const float dboff = p.db_offset - 16.0f * DB_PER_LOG2;
+        float* const out_db = p.db;                          // kernel parameters, read once
+        float* const out_power = p.power;
+        uint8_t* const out_u8 = p.db_u8;
         for (uint32_t it = 0; it < n_mine; ++it) {
             const size_t row_base = (size_t) (item_begin + it) * N64K;
             mbar_wait(z_full, it & 1);
@@ -354,34 +388,43 @@ __global__ void __launch_bounds__(C64_THREADS, 1) spectrum64k_cluster_kernel(con
                     }
                 }
                 const int k = 256 * (int) rank + kl;
+                float pw[64];
 #pragma unroll
                 for (int q = 0; q < 64; ++q) {
                     float re, im;
                     cunpack(z[q], re, im);
-                    const float pw = fmaf(re, re, im * im);
-                    const float db = fmaf(DB_PER_LOG2, lg2_ftz(pw), dboff);
-                    // fftshift (spectrum.c:25); bin N-1 also supplies the DC position (spectrum.c:30-33 with K = 1)
-                    const bool last = (k == 1023 && q == 63);
-                    const bool first = (k == 0 && q == 0);
-                    const size_t at = row_base + (size_t) (1024 * ((q + 32) & 63) + k);
-                    if (!first) {
-                        if (p.db) __stcs(p.db + at, db);
-                        if (p.power) __stcs(p.power + at, pw * FFT1024_POWER_SCALE);
-                        if (p.db_u8) {
-                            int m = __float2int_rz(db);
-                            m = m < 0 ? 0 : (m > 255 ? 255 : m);
-                            p.db_u8[at] = (uint8_t) m;
-                        }
+                    pw[q] = fmaf(re, re, im * im);
+                }
+                // fftshift (spectrum.c:25): bin k + 1024 q shows at column 1024 ((q + 32) & 63) + k -- a compile-time
+                // offset from one pointer per output array.  Bin 0 is not stored (the DC position shows bin N-1's value,
+                // spectrum.c:30-33 with K = 1): the thread that owns bin N-1 writes it.
+                const bool owns_first = (k == 0), owns_last = (k == 1023);
+                if (out_db != nullptr) {
+                    float* o = out_db + row_base + k;
+#pragma unroll
+                    for (int q = 0; q < 64; ++q) {
+                        const float db = fmaf(DB_PER_LOG2, lg2_ftz(pw[q]), dboff);
+                        if (q != 0 || !owns_first) __stcs(o + 1024 * ((q + 32) & 63), db);
+                        if (q == 63 && owns_last) __stcs(out_db + row_base + N64K / 2, db);
                     }
-                    if (last) {
-                        const size_t dc = row_base + N64K / 2;
-                        if (p.db) __stcs(p.db + dc, db);
-                        if (p.power) __stcs(p.power + dc, pw * FFT1024_POWER_SCALE);
-                        if (p.db_u8) {
-                            int m = __float2int_rz(db);
-                            m = m < 0 ? 0 : (m > 255 ? 255 : m);
-                            p.db_u8[dc] = (uint8_t) m;
-                        }
+                }
+                if (out_power != nullptr) {
+                    float* o = out_power + row_base + k;
+#pragma unroll
+                    for (int q = 0; q < 64; ++q) {
+                        const float v = pw[q] * FFT1024_POWER_SCALE;
+                        if (q != 0 || !owns_first) __stcs(o + 1024 * ((q + 32) & 63), v);
+                        if (q == 63 && owns_last) __stcs(out_power + row_base + N64K / 2, v);
+                    }
+                }
+                if (out_u8 != nullptr) {
+                    uint8_t* o = out_u8 + row_base + k;
+#pragma unroll
+                    for (int q = 0; q < 64; ++q) {
+                        int m = __float2int_rz(fmaf(DB_PER_LOG2, lg2_ftz(pw[q]), dboff));
+                        m = m < 0 ? 0 : (m > 255 ? 255 : m);
+                        if (q != 0 || !owns_first) o[1024 * ((q + 32) & 63)] = (uint8_t) m;
+                        if (q == 63 && owns_last) out_u8[row_base + N64K / 2] = (uint8_t) m;
                     }
                 }
                 // the input of frame it + 2: as soon as the producers have emptied the buffers, at the latest now
