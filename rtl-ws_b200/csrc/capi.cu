@@ -391,7 +391,7 @@ static int spectrum_exec_kind(b200_spectrum_plan* plan, const void* d_in, int64_
         p.twiddle_n = four_step ? plan->d_twiddle : plan->d_twiddle_rk;
         if (four_step) {
             // B200_S64K_CLUSTER=1 selects the four-CTA cluster kernel (Z in distributed shared memory, K = 1 rows;
-            // spectrum64k_cluster.cu): DRAM traffic 1.0x algorithmic but 90 vs 125 Gsamples/s, so it is not the default.
+            // spectrum64k_cluster.cu): DRAM traffic 1.0x algorithmic but 111 vs 123 Gsamples/s, so it is not the default.
             const char* env = getenv("B200_S64K_CLUSTER");
             if (plan->N == 65536 && plan->K == 1 && env != nullptr && atoi(env) != 0)
                 return launch_spectrum64k_cluster(p, plan->x64, stream);
