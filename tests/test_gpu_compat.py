@@ -153,6 +153,45 @@ def test_session_host_buffers(pkg, cuda, po, synth):
     sess.close()
 
 
+def test_session_products_host_buffers(pkg, cuda, po, synth):
+    """b200_session_products (what bench.py times as e2e_products): host IQ in, the reference's OWN products back --
+    the FM audio and, per stream, the payload bytes of the 6-frame average at the start of the batch
+    (cbb_main.c:40-70 + 106-135) -- two batches with the history carried inside, a gain, and argument errors."""
+    torch = cuda
+    n_streams, n, gain = 5, 5120 * 8, 17
+    iq = np.stack([synth.s2_tones(2 * n, seed=400 + s) for s in range(n_streams)])
+    sess = pkg.Session(n_streams, n)
+    h_iq = torch.empty((n_streams, n, 2), dtype=torch.uint8).pin_memory()
+    h_audio = torch.empty((n_streams, n // 40), dtype=torch.float32).pin_memory()
+    h_pay = torch.empty((n_streams, 1024), dtype=torch.uint8).pin_memory()
+    audio_parts = []
+    for b in range(2):
+        h_iq.copy_(torch.as_tensor(iq[:, b * n:(b + 1) * n]))
+        sess.products(h_iq, n, h_audio, h_pay, gain_db=gain, K_avg=6)
+        audio_parts.append(h_audio.numpy().copy())
+        for s in range(n_streams):
+            rows = po.Spectrum(1024).rows(iq[s, b * n:b * n + 6 * 1024], K=6)
+            want, dbf = po.db_payload(rows[0], 6, gain)
+            diff = h_pay.numpy()[s] != want
+            assert diff.mean() < 0.01 and (np.abs(dbf[diff] - np.rint(dbf[diff])) <= 0.01).all()
+    got = np.concatenate(audio_parts, axis=1)
+    for s in range(n_streams):
+        _, dec, _ = po.cic_decimate(10, iq[s])
+        _, _, want, _ = po.fm_demodulate(dec)
+        assert np.abs(got[s] - want).max() <= 1e-4
+    # the same batches through b200_session_chain give the same audio, bit for bit
+    sess.reset()
+    h_db = torch.empty((n_streams, n // 1024, 1024), dtype=torch.float32).pin_memory()
+    h_iq.copy_(torch.as_tensor(iq[:, :n]))
+    sess.chain(h_iq, n, h_db, h_audio, gain_db=gain)
+    assert np.array_equal(h_audio.numpy(), audio_parts[0])
+    with pytest.raises(pkg.B200Error):
+        sess.products(h_iq, n, h_audio, None)                  # the payload buffer is what the call is for
+    with pytest.raises(pkg.B200Error):
+        sess.products(h_iq, n, h_audio, h_pay, K_avg=0)
+    sess.close()
+
+
 @pytest.mark.parametrize("R", [12, 5, 16])
 def test_session_and_stream_other_down_factors(pkg, cuda, po, synth, R):
     """The reference re-derives R = fs / 192000 when the client sends `bw` (main.c:152-155): the fast-path
