@@ -274,6 +274,8 @@ def test_comm_gather_single_rank_and_sharding_helpers(pkg, cuda):
     assert [pkg.shard_stream(10, 4, 1, i) for i in range(3)] == [1, 5, 9]
     assert pkg.lib().b200_comm_nccl_version() > 20000
     comm = pkg.Comm(pkg.Comm.unique_id(), 1, 0)
+    assert pkg.lib().b200_comm_world(comm.h) == 1 and pkg.lib().b200_comm_rank(comm.h) == 0
+    assert pkg.lib().b200_comm_world(None) < 0 and pkg.lib().b200_shard_count(10, 4, 4) < 0 and pkg.lib().b200_shard_stream(10, 4, 1, 3) < 0
     send = torch.randint(0, 256, (7, 1024), dtype=torch.uint8, device="cuda")
     recv = torch.zeros_like(send)
     comm.gather_rows(send, 7, recv)

@@ -153,6 +153,26 @@ def test_session_host_buffers(pkg, cuda, po, synth):
     sess.close()
 
 
+def test_host_alloc_is_pinned_and_sm_count(pkg, cuda):
+    """b200_host_alloc hands out page-locked memory (what makes the session's copies asynchronous); b200_sm_count is the
+    device's SM count (148 on a B200: the persistent kernels size their grids with it)."""
+    import ctypes as C
+    torch = cuda
+    L = pkg.lib()
+    ptr = L.b200_host_alloc(1 << 20)
+    assert ptr
+    buf = (C.c_ubyte * (1 << 20)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=np.uint8)
+    arr[:] = 7
+    t = torch.from_numpy(arr)
+    d = t.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+    assert int(d.sum()) == 7 << 20
+    del t, d, arr, buf
+    L.b200_host_free(ptr)
+    assert L.b200_sm_count() == torch.cuda.get_device_properties(0).multi_processor_count
+
+
 def test_session_products_host_buffers(pkg, cuda, po, synth):
     """b200_session_products (what bench.py times as e2e_products): host IQ in, the reference's OWN products back --
     the FM audio and, per stream, the payload bytes of the 6-frame average at the start of the batch
